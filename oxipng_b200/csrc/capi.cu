@@ -1,0 +1,487 @@
+// capi.cu -- the C ABI (include/oxipng_b200.h): host-side geometry, per-device contexts, tier dispatch and
+// host<->device staging for the filter-search entry points.  No CPU compute path exists here: when CUDA is
+// unavailable every compute entry point returns OXI_E_CUDA.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace oxi {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+thread_local std::string t_err;
+thread_local int t_device = 0;
+
+int fail(int code, const char *msg) {
+    t_err = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char *where) {
+    t_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return OXI_E_CUDA;
+}
+
+// ---- geometry -------------------------------------------------------------------------------------------
+
+size_t channels(uint8_t ct) {
+    switch (ct) { // src/colors.rs:59-66
+    case 0: case 3: return 1;
+    case 4: return 2;
+    case 2: return 3;
+    case 6: return 4;
+    default: return 0;
+    }
+}
+
+bool valid_ihdr(const oxi_ihdr *h) {
+    if (!h || h->width == 0 || h->height == 0) return false;
+    if (channels(h->color_type) == 0) return false;
+    switch (h->bit_depth) {
+    case 1: case 2: case 4: return h->color_type == 0 || h->color_type == 3;
+    case 8: return true;
+    case 16: return h->color_type != 3;
+    default: return false;
+    }
+}
+
+// Adam7 pass origin/stride (src/interlace.rs:186-232)
+static const uint32_t kX0[7] = {0, 4, 0, 2, 0, 1, 0}, kY0[7] = {0, 0, 4, 0, 2, 0, 1};
+static const uint32_t kDX[7] = {8, 8, 4, 4, 2, 2, 1}, kDY[7] = {8, 8, 8, 4, 4, 2, 2};
+
+// The rows ScanLines (src/png/scan_lines.rs:82-167) yields for `data_len` bytes, grouped by pass.  The iterator's
+// per-pass pixel counts and its skipping of empty passes equal ceil((W-x0)/dx) x ceil((H-y0)/dy) with empty passes
+// dropped (checked exhaustively against the oracle's state machine in tests/test_geometry.py); it stops as soon as
+// the remaining bytes cannot hold another row, and a non-interlaced image keeps yielding rows while bytes remain.
+bool build_geom(const oxi_ihdr *h, size_t data_len, int optimize_alpha, Geom *g) {
+    memset(g, 0, sizeof *g);
+    if (!valid_ihdr(h)) return false;
+    const size_t bits = (size_t)h->bit_depth * channels(h->color_type);
+    const size_t bpc = h->bit_depth == 16 ? 2 : 1;
+    g->bpp = (uint32_t)(bpc * channels(h->color_type));
+    const bool alpha = h->color_type == 4 || h->color_type == 6;
+    g->alpha_bytes = (optimize_alpha && alpha) ? (uint32_t)bpc : 0; // src/png/mod.rs:363-367
+    g->color_bytes = g->bpp - g->alpha_bytes;
+    size_t left = data_len, off = 0;
+    uint32_t row = 0;
+    if (!h->interlaced) {
+        const size_t len = ((size_t)h->width * bits + 7) / 8;
+        if (len > 0xFFFFFFFFu) return false;
+        const size_t n = left / len;
+        if (n > 0xFFFFFFFFu) return false;
+        if (n) {
+            g->pass[0] = PassDesc{0, (uint32_t)n, (uint32_t)len, 0, 0};
+            g->n_pass = 1;
+            g->max_len = (uint32_t)len;
+            row = (uint32_t)n;
+            off = n * len;
+        }
+    } else {
+        for (int p = 0; p < 7; p++) {
+            if (h->width <= kX0[p] || h->height <= kY0[p]) continue;
+            const size_t pw = ((size_t)h->width - kX0[p] + kDX[p] - 1) / kDX[p];
+            const size_t ph = ((size_t)h->height - kY0[p] + kDY[p] - 1) / kDY[p];
+            const size_t len = (pw * bits + 7) / 8;
+            if (len > 0xFFFFFFFFu) return false;
+            size_t n = left / len;
+            const bool exhausted = n < ph;
+            if (n > ph) n = ph;
+            if (n) {
+                g->pass[g->n_pass++] = PassDesc{row, (uint32_t)n, (uint32_t)len, 0, (uint64_t)off};
+                if (len > g->max_len) g->max_len = (uint32_t)len;
+                row += (uint32_t)n;
+                off += n * len;
+                left -= n * len;
+            }
+            if (exhausted) break;
+        }
+    }
+    g->total_rows = row;
+    g->data_len = off;
+    g->out_len = off + row;
+    return true;
+}
+
+// ---- per-device context -----------------------------------------------------------------------------------
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint8_t *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    uint8_t *d_in = nullptr;
+    size_t in_cap = 0;
+    uint8_t *d_out = nullptr; // all strategies' outputs + filters_used, carved
+    size_t out_cap = 0;
+    uint8_t *d_pre = nullptr; // predefined filter ids
+    size_t pre_cap = 0;
+};
+
+struct DeviceCtx {
+    int device = -1;
+    int num_sms = 0;
+    std::mutex mu;
+    std::vector<Slot *> free_slots;
+    std::map<cudaStream_t, Slot *> stream_slots;
+};
+
+static std::mutex g_ctx_mu;
+static std::map<int, DeviceCtx *> g_ctx;
+
+DeviceCtx *get_ctx(int device, int *err) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    auto it = g_ctx.find(device);
+    if (it != g_ctx.end()) return it->second;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *err = fail_cuda(e, "cudaGetDeviceCount"); return nullptr; }
+    if (device < 0 || device >= n) { *err = fail(OXI_E_CUDA, "no such CUDA device"); return nullptr; }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { *err = fail_cuda(e, "cudaGetDeviceProperties"); return nullptr; }
+    if (prop.major < 10) { *err = fail(OXI_E_CUDA, "device is not sm_100 class"); return nullptr; }
+    DeviceCtx *c = new DeviceCtx;
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    g_ctx[device] = c;
+    return c;
+}
+
+static cudaError_t grow(uint8_t **p, size_t *cap, size_t need) {
+    if (need <= *cap) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 4 + 4096;
+    cudaError_t e = cudaMalloc((void **)p, want);
+    if (e == cudaSuccess) *cap = want;
+    return e;
+}
+
+Slot *acquire_slot(DeviceCtx *c) {
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->free_slots.empty()) {
+            Slot *s = c->free_slots.back();
+            c->free_slots.pop_back();
+            return s;
+        }
+    }
+    Slot *s = new Slot;
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return nullptr; }
+    s->own_stream = true;
+    return s;
+}
+void release_slot(DeviceCtx *c, Slot *s) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->free_slots.push_back(s);
+}
+// Slot bound to a caller stream (device-resident API): scratch reuse is then ordered by that stream.
+Slot *stream_slot(DeviceCtx *c, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->stream_slots.find(st);
+    if (it != c->stream_slots.end()) return it->second;
+    Slot *s = new Slot;
+    s->stream = st;
+    c->stream_slots[st] = s;
+    return s;
+}
+
+// ---- dispatch -----------------------------------------------------------------------------------------------
+
+bool valid_strategy(const oxi_strategy *s) {
+    if (!s) return false;
+    if (s->kind > OXI_PREDEFINED) return false;
+    if (s->kind == OXI_BASIC && s->basic_filter > 4) return false;
+    if (s->kind == OXI_PREDEFINED) {
+        if (s->n_predefined && !s->predefined) return false;
+        for (size_t i = 0; i < s->n_predefined; i++)
+            if (s->predefined[i] > 4) return false;
+    }
+    return true;
+}
+
+// Upload Predefined lists (stream ordered) and fill the kernel-side strategy set.
+int make_set(Slot *slot, const oxi_strategy *st, size_t k, uint8_t *const *d_outs, uint8_t *const *d_used,
+             StrategySet *set) {
+    if (k == 0 || k > (size_t)MAX_STRATEGIES) return fail(OXI_E_ARG, "strategy count must be 1..8");
+    size_t pre_total = 0;
+    for (size_t j = 0; j < k; j++) {
+        if (!valid_strategy(&st[j])) return fail(OXI_E_ARG, "invalid strategy");
+        if (st[j].kind == OXI_PREDEFINED) pre_total += st[j].n_predefined;
+    }
+    if (pre_total) {
+        cudaError_t e = grow(&slot->d_pre, &slot->pre_cap, pre_total);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(predefined)");
+    }
+    set->k = (int)k;
+    size_t off = 0;
+    for (size_t j = 0; j < k; j++) {
+        DevStrategy &d = set->s[j];
+        d.kind = st[j].kind;
+        d.basic = st[j].basic_filter;
+        d.predefined = nullptr;
+        d.n_predefined = 0;
+        if (st[j].kind == OXI_PREDEFINED && st[j].n_predefined) {
+            size_t n = st[j].n_predefined > 0xFFFFFFFFu ? 0xFFFFFFFFu : st[j].n_predefined;
+            cudaError_t e = cudaMemcpyAsync(slot->d_pre + off, st[j].predefined, n, cudaMemcpyHostToDevice, slot->stream);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(predefined)");
+            d.predefined = slot->d_pre + off;
+            d.n_predefined = (uint32_t)n;
+            off += n;
+        }
+        d.out = d_outs[j];
+        d.filters_used = d_used[j];
+    }
+    return OXI_OK;
+}
+
+bool want_fast(const Geom &g, const StrategySet &set, unsigned flags) {
+    if (flags & OXI_FLAG_FORCE_GENERIC) return false;
+    return fast_supported(g, set);
+}
+
+int run_filters(DeviceCtx *c, Slot *slot, const Geom &g, const uint8_t *d_data, size_t n_images, const StrategySet &set,
+                unsigned flags) {
+    if (g.total_rows == 0 || n_images == 0) return OXI_OK;
+    LaunchCtx lc;
+    lc.device = c->device;
+    lc.stream = slot->stream;
+    lc.num_sms = c->num_sms;
+    cudaError_t e;
+    if (want_fast(g, set, flags)) {
+        lc.scratch = nullptr;
+        lc.scratch_bytes = 0;
+        e = launch_fast(lc, g, d_data, n_images, set);
+        if (e != cudaSuccess) return fail_cuda(e, "launch_fast");
+        return OXI_OK;
+    }
+    if (flags & OXI_FLAG_FORCE_FAST) return fail(OXI_E_UNSUPPORTED, "fast tier does not cover this call");
+    size_t need = generic_scratch_bytes(g, n_images, c->num_sms, nullptr);
+    e = grow(&slot->scratch, &slot->scratch_bytes, need);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(scratch)");
+    lc.scratch = slot->scratch;
+    lc.scratch_bytes = slot->scratch_bytes;
+    e = launch_generic(lc, g, d_data, n_images, set);
+    if (e != cudaSuccess) return fail_cuda(e, "launch_generic");
+    return OXI_OK;
+}
+
+// Host-buffer path for a contiguous batch chunk: upload, filter with all k strategies, download.
+int filter_host_chunk(DeviceCtx *c, Slot *slot, const Geom &g, const uint8_t *data, size_t stride_in, size_t n_images,
+                      const oxi_strategy *st, size_t k, uint8_t *const *outs, uint8_t *const *used, unsigned flags,
+                      bool sync) {
+    cudaError_t e = grow(&slot->d_in, &slot->in_cap, n_images * (size_t)g.data_len + 64);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(input)");
+    const size_t per_out = n_images * (size_t)g.out_len, per_used = n_images * (size_t)g.total_rows;
+    const size_t out_stride = (per_out + 255) & ~(size_t)255, used_stride = (per_used + 255) & ~(size_t)255;
+    e = grow(&slot->d_out, &slot->out_cap, k * (out_stride + used_stride) + 64);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(output)");
+    uint8_t *d_outs[MAX_STRATEGIES], *d_used[MAX_STRATEGIES];
+    for (size_t j = 0; j < k && j < (size_t)MAX_STRATEGIES; j++) {
+        d_outs[j] = slot->d_out + j * (out_stride + used_stride);
+        d_used[j] = d_outs[j] + out_stride;
+    }
+    StrategySet set;
+    int rc = make_set(slot, st, k, d_outs, d_used, &set);
+    if (rc) return rc;
+    if (stride_in == g.data_len) {
+        e = cudaMemcpyAsync(slot->d_in, data, n_images * (size_t)g.data_len, cudaMemcpyHostToDevice, slot->stream);
+    } else {
+        e = cudaMemcpy2DAsync(slot->d_in, g.data_len, data, stride_in, g.data_len, n_images, cudaMemcpyHostToDevice,
+                              slot->stream);
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(H2D)");
+    rc = run_filters(c, slot, g, slot->d_in, n_images, set, flags);
+    if (rc) return rc;
+    for (size_t j = 0; j < k; j++) {
+        if (outs && outs[j]) {
+            e = cudaMemcpyAsync(outs[j], d_outs[j], per_out, cudaMemcpyDeviceToHost, slot->stream);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(D2H out)");
+        }
+        if (used && used[j]) {
+            e = cudaMemcpyAsync(used[j], d_used[j], per_used, cudaMemcpyDeviceToHost, slot->stream);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(D2H filters)");
+        }
+    }
+    if (sync) {
+        e = cudaStreamSynchronize(slot->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize");
+    }
+    return OXI_OK;
+}
+
+} // namespace oxi
+
+using namespace oxi;
+
+extern "C" {
+
+const char *oxi_last_error(void) { return t_err.c_str(); }
+const char *oxi_version(void) { return "oxipng-b200 0.1.0 (sm_100a)"; }
+int oxi_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int oxi_set_device(int device) {
+    int err = 0;
+    if (!get_ctx(device, &err)) return err;
+    t_device = device;
+    return OXI_OK;
+}
+uint64_t oxi_kernel_launches(void) { return g_launches.load(); }
+
+size_t oxi_bits_per_pixel(const oxi_ihdr *h) { return h ? (size_t)h->bit_depth * channels(h->color_type) : 0; }
+size_t oxi_filter_bpp(const oxi_ihdr *h) { return h ? (h->bit_depth == 16 ? 2 : 1) * channels(h->color_type) : 0; }
+
+size_t oxi_raw_data_size(const oxi_ihdr *h) { // src/headers.rs:38-64
+    if (!h) return 0;
+    const size_t w = h->width, ht = h->height, bpp = oxi_bits_per_pixel(h);
+    auto bitmap = [bpp](size_t pw, size_t ph) { return ((pw * bpp + 7) / 8) * ph; };
+    if (!h->interlaced) return bitmap(w, ht) + ht;
+    size_t size = bitmap((w + 7) >> 3, (ht + 7) >> 3) + ((ht + 7) >> 3);
+    if (w > 4) size += bitmap((w + 3) >> 3, (ht + 7) >> 3) + ((ht + 7) >> 3);
+    size += bitmap((w + 3) >> 2, (ht + 3) >> 3) + ((ht + 3) >> 3);
+    if (w > 2) size += bitmap((w + 1) >> 2, (ht + 3) >> 2) + ((ht + 3) >> 2);
+    size += bitmap((w + 1) >> 1, (ht + 1) >> 2) + ((ht + 1) >> 2);
+    if (w > 1) size += bitmap(w >> 1, (ht + 1) >> 1) + ((ht + 1) >> 1);
+    return size + bitmap(w, ht >> 1) + (ht >> 1);
+}
+
+size_t oxi_num_scanlines(const oxi_ihdr *h, size_t data_len) {
+    Geom g;
+    if (!build_geom(h, data_len, 0, &g)) return 0;
+    return g.total_rows;
+}
+
+size_t oxi_scan_lines(const oxi_ihdr *h, size_t data_len, uint32_t *len, uint8_t *pass, uint32_t *pixels, size_t cap) {
+    Geom g;
+    if (!build_geom(h, data_len, 0, &g)) return 0;
+    const size_t bits = oxi_bits_per_pixel(h);
+    size_t n = 0;
+    int pid = 0;
+    for (uint32_t p = 0; p < g.n_pass; p++) {
+        uint8_t pass_id = 0;
+        uint32_t px = h->width;
+        if (h->interlaced) {
+            // recover the pass number: passes appear in order, empty ones skipped
+            while (pid < 7 && (h->width <= kX0[pid] || h->height <= kY0[pid])) pid++;
+            pass_id = (uint8_t)(pid + 1);
+            px = (h->width - kX0[pid] + kDX[pid] - 1) / kDX[pid];
+            pid++;
+        }
+        (void)bits;
+        for (uint32_t k = 0; k < g.pass[p].nrows; k++, n++) {
+            if (n < cap) {
+                if (len) len[n] = g.pass[p].len;
+                if (pass) pass[n] = pass_id;
+                if (pixels) pixels[n] = px;
+            }
+        }
+    }
+    return n;
+}
+
+const char *oxi_filter_tier(const oxi_ihdr *h, size_t data_len, const oxi_strategy *st, int optimize_alpha) {
+    Geom g;
+    if (!build_geom(h, data_len, optimize_alpha, &g) || !valid_strategy(st)) return "invalid";
+    StrategySet set;
+    memset(&set, 0, sizeof set);
+    set.k = 1;
+    set.s[0].kind = st->kind;
+    set.s[0].basic = st->basic_filter;
+    return fast_supported(g, set) ? "fast" : "generic";
+}
+
+int oxi_filter_batch_device(int device, void *stream, const oxi_ihdr *h, const uint8_t *d_data, size_t data_len,
+                            size_t n_images, const oxi_strategy *strategies, size_t k, int optimize_alpha,
+                            uint8_t *const *d_outs, uint8_t *const *d_filters_used, unsigned flags) {
+    Geom g;
+    if (!build_geom(h, data_len, optimize_alpha, &g)) return fail(OXI_E_ARG, "invalid IHDR");
+    if (g.data_len != data_len) return fail(OXI_E_ARG, "data_len is not a whole number of scanlines for this IHDR");
+    if (!d_data || !d_outs || !d_filters_used || !strategies) return fail(OXI_E_ARG, "null pointer");
+    int err = 0;
+    DeviceCtx *c = get_ctx(device, &err);
+    if (!c) return err;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
+    Slot *slot = stream_slot(c, (cudaStream_t)stream);
+    StrategySet set;
+    int rc = make_set(slot, strategies, k, d_outs, d_filters_used, &set);
+    if (rc) return rc;
+    return run_filters(c, slot, g, d_data, n_images, set, flags);
+}
+
+int oxi_filter_batch(const oxi_ihdr *h, const uint8_t *data, size_t data_len, size_t n_images,
+                     const oxi_strategy *strategies, size_t k, int optimize_alpha, uint8_t *const *outs,
+                     uint8_t *const *filters_used, unsigned flags) {
+    Geom g;
+    if (!build_geom(h, data_len, optimize_alpha, &g)) return fail(OXI_E_ARG, "invalid IHDR");
+    if (!data || !strategies || k == 0 || k > (size_t)MAX_STRATEGIES) return fail(OXI_E_ARG, "bad arguments");
+    int err = 0;
+    DeviceCtx *c = get_ctx(t_device, &err);
+    if (!c) return err;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
+    if (n_images == 0) return OXI_OK;
+    // chunk the batch so uploads, kernels and downloads of neighbouring chunks overlap (3 slots in flight)
+    const size_t target = (size_t)96 << 20;
+    size_t per = g.data_len ? target / (size_t)g.data_len : n_images;
+    if (per < 1) per = 1;
+    if (per > n_images) per = n_images;
+    const size_t n_chunks = (n_images + per - 1) / per;
+    const int NS = n_chunks >= 3 ? 3 : (int)n_chunks;
+    Slot *slots[3] = {nullptr, nullptr, nullptr};
+    int rc = OXI_OK;
+    for (int i = 0; i < NS; i++) {
+        slots[i] = acquire_slot(c);
+        if (!slots[i]) rc = fail(OXI_E_CUDA, "cannot create stream");
+    }
+    for (size_t ci = 0; ci < n_chunks && rc == OXI_OK; ci++) {
+        Slot *s = slots[ci % NS];
+        if (ci >= (size_t)NS) { // buffers of this slot are still in use by chunk ci-NS
+            e = cudaStreamSynchronize(s->stream);
+            if (e != cudaSuccess) { rc = fail_cuda(e, "cudaStreamSynchronize"); break; }
+        }
+        const size_t i0 = ci * per, n = (i0 + per <= n_images) ? per : n_images - i0;
+        uint8_t *o[MAX_STRATEGIES], *u[MAX_STRATEGIES];
+        for (size_t j = 0; j < k; j++) {
+            o[j] = (outs && outs[j]) ? outs[j] + i0 * (size_t)g.out_len : nullptr;
+            u[j] = (filters_used && filters_used[j]) ? filters_used[j] + i0 * (size_t)g.total_rows : nullptr;
+        }
+        rc = filter_host_chunk(c, s, g, data + i0 * data_len, data_len, n, strategies, k, o, u, flags, false);
+    }
+    for (int i = 0; i < NS; i++) {
+        if (!slots[i]) continue;
+        e = cudaStreamSynchronize(slots[i]->stream);
+        if (e != cudaSuccess && rc == OXI_OK) rc = fail_cuda(e, "cudaStreamSynchronize");
+        release_slot(c, slots[i]);
+    }
+    return rc;
+}
+
+int oxi_filter_image_multi(const oxi_ihdr *h, const uint8_t *data, size_t data_len, const oxi_strategy *strategies,
+                           size_t k, int optimize_alpha, uint8_t *const *outs, uint8_t *const *filters_used) {
+    return oxi_filter_batch(h, data, data_len, 1, strategies, k, optimize_alpha, outs, filters_used, 0);
+}
+
+int oxi_filter_image(const oxi_ihdr *h, const uint8_t *data, size_t data_len, const oxi_strategy *strategy,
+                     int optimize_alpha, uint8_t *out, uint8_t *filters_used, int *used_is_predefined) {
+    if (!strategy) return fail(OXI_E_ARG, "null strategy");
+    uint8_t *outs[1] = {out}, *used[1] = {filters_used};
+    int rc = oxi_filter_batch(h, data, data_len, 1, strategy, 1, optimize_alpha, outs, used, 0);
+    if (rc == OXI_OK && used_is_predefined) { // src/png/mod.rs:426-430
+        const bool heuristic = strategy->kind != OXI_BASIC && strategy->kind != OXI_PREDEFINED;
+        *used_is_predefined = heuristic && oxi_num_scanlines(h, data_len) > 0;
+    }
+    return rc;
+}
+
+} // extern "C"
