@@ -210,7 +210,7 @@ bool valid_strategy(const oxi_strategy *s) {
 // Upload Predefined lists (stream ordered) and fill the kernel-side strategy set.
 int make_set(Slot *slot, const oxi_strategy *st, size_t k, uint8_t *const *d_outs, uint8_t *const *d_used,
              StrategySet *set) {
-    if (k == 0 || k > (size_t)MAX_STRATEGIES) return fail(OXI_E_ARG, "strategy count must be 1..8");
+    if (k == 0 || k > (size_t)MAX_STRATEGIES) return fail(OXI_E_ARG, "strategy count must be 1..12");
     size_t pre_total = 0;
     for (size_t j = 0; j < k; j++) {
         if (!valid_strategy(&st[j])) return fail(OXI_E_ARG, "invalid strategy");

@@ -44,7 +44,7 @@ struct DevStrategy {
     uint8_t *filters_used; // n_images * total_rows
 };
 
-constexpr int MAX_STRATEGIES = 8;
+constexpr int MAX_STRATEGIES = 12; // -o6 evaluates 9 in-scope strategies at once (options.rs:250-273)
 
 struct StrategySet {
     int k;

@@ -1,8 +1,649 @@
-// filter_fast.cu -- fast tier (placeholder until the sm_100a kernels land)
+// filter_fast.cu -- fast tier of PngImage::filter_image (src/png/mod.rs:355-431) for sm_100a.
+//
+// One kernel family, `k_fast<D, SC>`.  A CTA takes a *band* of consecutive scanlines of one pass of one image and
+// walks it row by row; rows are staged in a 3-slot shared-memory ring by 1-D TMA bulk copies (cp.async.bulk +
+// mbarrier) so the next row streams in while the current one is scored, and the previous row stays resident
+// (each row is read from HBM once, plus one halo row per band).  Per row:
+//   1. all five RowFilters are applied with byte-SIMD arithmetic on 128-bit shared-memory loads
+//      (src/filters/mod.rs:63-110; Paeth :242-254 in a branch-free byte form) and scored:
+//        MinSum  (strategies.rs:76-101)   VABSDIFF4 + accumulate: |r as i8| = 128 - ||cur-pred| - 128|
+//        Entropy (strategies.rs:105-149)  five 256-bin shared-memory histograms (x HIST_REP copies), ATOMS.ADD
+//        Bigrams (strategies.rs:153-192)  } one 65536 x u16 shared-memory counter table shared by the five trials;
+//        BigEnt  (strategies.rs:195-227)  } the thread whose add sees 0 owns the bigram, reads the final count after
+//                                           the barrier (distinct += 1, entropy += ilog2i(count)) and clears it
+//   2. the winner per strategy is picked with the reference's strict comparisons in RowFilter::ALL order
+//      (lowest filter id wins ties; all-zero rows short-circuit to None, png/mod.rs:398-404),
+//   3. only the chosen filtered row is written: recomputed in the *output-aligned* frame so that every store is a
+//      16-byte st.global.v4 (rows of the filtered stream start at r*(len+1), never aligned).
+// Requirements: alpha_bytes == 0 (rows independent given the previous raw row) and 3 staged rows (+ tables) must
+// fit in 227 KB of shared memory; everything else goes to the generic tier.
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
+
 namespace oxi {
-bool fast_supported(const Geom &, const StrategySet &) { return false; }
-cudaError_t launch_fast(const LaunchCtx &, const Geom &, const uint8_t *, size_t, const StrategySet &) {
-    return cudaErrorNotSupported;
+
+namespace {
+
+constexpr int SC_MINSUM = 1, SC_ENTROPY = 2, SC_BIGRAM = 4;
+constexpr int HIST_REP = 4;      // copies of each Entropy histogram (lane & 3) to thin same-address atomics
+constexpr uint32_t PAD = 32;     // zero bytes in front of every staged row (left/upleft of the first pixel)
+constexpr uint32_t SMEM_HDR = 512;
+constexpr uint32_t SMEM_LIMIT = 232448; // 227 KB
+
+struct FastParams {
+    Geom g;
+    StrategySet set;
+    const uint8_t *data;
+    uint64_t n_images;
+    uint32_t band_start[8]; // prefix sum of bands per pass
+    uint32_t items_per_image;
+    uint32_t rb;    // bytes of one ring slot
+    uint32_t shift; // 8 * (bpp % 4): funnel-shift amount that turns a row word into its "left" word
+};
+
+__host__ __device__ constexpr int threads_for(int sc) { return (sc & SC_BIGRAM) ? 1024 : 256; }
+
+// ---- PTX wrappers: mbarrier + 1-D bulk tensor-memory-accelerator copy -----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\t"
+                 "bra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- byte-SIMD helpers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t signmask4(uint32_t x) { return __byte_perm(x, 0, 0xba98); } // 0xFF where MSB set
+__device__ __forceinline__ uint32_t sel4(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
+
+// paeth_predictor (src/filters/mod.rs:242-254) on four byte lanes, without widening.
+// a=left, b=up, c=upleft.  pa=|b-c|, pb=|a-c|.  pc=|a+b-2c| equals |pa-pb| when c lies between a and b and pa+pb
+// (>= both) otherwise; "otherwise" is detected as |pa-pb| == |a-b| and pc saturated to 255, which keeps both
+// comparisons against pc true.  Then the winner is the closer of a/b (ties -> a) if its distance <= pc, else c.
+// Checked exhaustively over all 2^24 (a,b,c) on the host.
+__device__ __forceinline__ uint32_t paeth4(uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t pa = __vabsdiffu4(b, c), pb = __vabsdiffu4(a, c);
+    const uint32_t pd = __vabsdiffu4(pa, pb);
+    const uint32_t pc = pd | __vcmpeq4(pd, __vabsdiffu4(a, b));
+    const uint32_t le = __vcmpleu4(pa, pb);
+    const uint32_t w = sel4(le, a, b), mn = sel4(le, pa, pb);
+    // mn <= pc: mn < 128 whenever pc < 255, so (pc|0x80)-mn never borrows and its MSB decides for pc < 128
+    const uint32_t t = (pc | 0x80808080u) - mn;
+    return sel4(signmask4(t | pc), w, c);
+}
+
+template <int F>
+__device__ __forceinline__ uint32_t pred4(uint32_t left, uint32_t up, uint32_t ul) {
+    if (F == 0) return 0u;
+    if (F == 1) return left;
+    if (F == 2) return up;
+    if (F == 3) return __vhaddu4(left, up); // floor((left+up)/2), filters/mod.rs:93
+    return paeth4(left, up, ul);
+}
+__device__ __forceinline__ uint32_t pred4_rt(int f, uint32_t left, uint32_t up, uint32_t ul) {
+    switch (f) {
+    case 0: return 0u;
+    case 1: return left;
+    case 2: return up;
+    case 3: return __vhaddu4(left, up);
+    default: return paeth4(left, up, ul);
+    }
+}
+
+// A 16-byte chunk of a staged row plus the 8 bytes before it: w[j] is row word (4*chunk + j - 2).
+struct Chunk {
+    uint32_t w[6];
+};
+__device__ __forceinline__ Chunk load_chunk(const uint8_t *row, uint32_t c) {
+    Chunk k;
+    const uint2 lo = *reinterpret_cast<const uint2 *>(row + 16 * (size_t)c - 8);
+    const uint4 hi = *reinterpret_cast<const uint4 *>(row + 16 * (size_t)c);
+    k.w[0] = lo.x; k.w[1] = lo.y; k.w[2] = hi.x; k.w[3] = hi.y; k.w[4] = hi.z; k.w[5] = hi.w;
+    return k;
+}
+// word k (0..3) of the chunk shifted right by bpp bytes: the "left" (or "upleft") neighbours of its four bytes.
+// D = bpp / 4, s = 8 * (bpp % 4).
+template <int D>
+__device__ __forceinline__ uint32_t left_word(const Chunk &c, int k, uint32_t s) {
+    if (D == 2) return c.w[k];
+    if (D == 1) return __funnelshift_l(c.w[k], c.w[k + 1], s);
+    return __funnelshift_l(c.w[k + 1], c.w[k + 2], s);
+}
+__device__ __forceinline__ uint32_t tail_mask(int valid_bytes) { // bytes of a word that lie inside the row
+    return valid_bytes >= 4 ? 0xFFFFFFFFu : (valid_bytes <= 0 ? 0u : ((1u << (8 * valid_bytes)) - 1u));
+}
+
+// 16 bytes starting at an arbitrary byte offset of a staged row (shared memory), via 32-bit loads + funnel shifts.
+__device__ __forceinline__ uint4 ld_unaligned16(const uint8_t *p) {
+    const uint32_t a = smem_u32(p);
+    const uint32_t s = (a & 3u) * 8u;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p - (a & 3u));
+    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+    uint4 r;
+    r.x = __funnelshift_r(w0, w1, s);
+    r.y = __funnelshift_r(w1, w2, s);
+    r.z = __funnelshift_r(w2, w3, s);
+    r.w = __funnelshift_r(w3, w4, s);
+    return r;
+}
+
+// scalar residual of row byte i (i >= 0) under filter f, reading the staged rows (left pads are zero)
+__device__ __forceinline__ uint32_t residual_at(int f, const uint8_t *cur, const uint8_t *up, int i, int bpp) {
+    return residual_byte(f, cur[i], cur[i - bpp], up[i], up[i - bpp]);
+}
+
+// ---- shared-memory carve-up --------------------------------------------------------------------------------------
+struct Smem {
+    uint64_t *bar;     // 3 mbarriers
+    uint32_t *s_min;   // [5] MinSum sad accumulators
+    uint32_t *s_ent;   // [5]
+    uint32_t *s_bgc;   // [5] distinct bigrams
+    uint32_t *s_bge;   // [5] bigram entropy
+    uint8_t *rows;     // 3 slots of rb bytes
+    uint32_t *hist;    // [5][HIST_REP][256]
+    uint32_t *table;   // 32768 words = 65536 u16 counters
+};
+template <int SC>
+__device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb) {
+    Smem s;
+    s.bar = reinterpret_cast<uint64_t *>(base);
+    uint32_t *u = reinterpret_cast<uint32_t *>(base + 64);
+    s.s_min = u; s.s_ent = u + 8; s.s_bgc = u + 16; s.s_bge = u + 24;
+    s.rows = base + SMEM_HDR;
+    uint8_t *p = s.rows + 3 * (size_t)rb;
+    s.hist = reinterpret_cast<uint32_t *>(p);
+    if (SC & SC_ENTROPY) p += 5 * HIST_REP * 256 * 4;
+    s.table = reinterpret_cast<uint32_t *>(p);
+    return s;
+}
+__host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb) {
+    uint32_t b = SMEM_HDR + 3 * rb;
+    if (sc & SC_ENTROPY) b += 5 * HIST_REP * 256 * 4;
+    if (sc & SC_BIGRAM) b += 65536 * 2;
+    return b;
+}
+
+// ---- scoring passes ------------------------------------------------------------------------------------------------
+
+// MinSum for all five filters in one sweep. Accumulates S_f = sum over bytes of ||cur-pred_f| - 128|; the caller turns
+// it into the reference's score 128*bytes - S_f + f (the filter-type byte f counts |f| = f, png/mod.rs:409-414).
+template <int D, int NT>
+__device__ __forceinline__ void minsum_pass(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
+                                            uint32_t *s_min) {
+    const uint32_t nchunks = (len + 15) >> 4;
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    const uint32_t H = 0x80808080u;
+    for (uint32_t c = threadIdx.x; c < nchunks; c += NT) {
+        const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
+        const int valid = (int)len - (int)(16 * c);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t x = cw.w[k + 2], u = uw.w[k + 2], l = left_word<D>(cw, k, shift), ul = left_word<D>(uw, k, shift);
+            if (valid < 16) { // last, partial chunk: bytes past the row contribute |0-0| -> cancel exactly
+                const uint32_t m = tail_mask(valid - 4 * k);
+                x &= m; u &= m; l &= m; ul &= m;
+            }
+            a0 = __vsadu4(x, H) + a0;
+            a1 = __vsadu4(__vabsdiffu4(x, l), H) + a1;
+            a2 = __vsadu4(__vabsdiffu4(x, u), H) + a2;
+            a3 = __vsadu4(__vabsdiffu4(x, __vhaddu4(l, u)), H) + a3;
+            a4 = __vsadu4(__vabsdiffu4(x, paeth4(l, u, ul)), H) + a4;
+        }
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_min[0], a0); atomicAdd(&s_min[1], a1); atomicAdd(&s_min[2], a2);
+        atomicAdd(&s_min[3], a3); atomicAdd(&s_min[4], a4);
+    }
+}
+
+__device__ __forceinline__ void hist_add4(uint32_t *h, uint32_t r, int nvalid) {
+    if (nvalid >= 4) {
+        atomicAdd(h + (r & 255u), 1u);
+        atomicAdd(h + ((r >> 8) & 255u), 1u);
+        atomicAdd(h + ((r >> 16) & 255u), 1u);
+        atomicAdd(h + (r >> 24), 1u);
+    } else {
+        for (int j = 0; j < nvalid; j++) atomicAdd(h + ((r >> (8 * j)) & 255u), 1u);
+    }
+}
+
+// Entropy: histogram the residual bytes of all five filters (filter-type byte added at scoring time).
+template <int D, int NT>
+__device__ __forceinline__ void entropy_pass(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
+                                             uint32_t *hist) {
+    const uint32_t nchunks = (len + 15) >> 4;
+    uint32_t *h = hist + (threadIdx.x & (HIST_REP - 1)) * 256;
+    for (uint32_t c = threadIdx.x; c < nchunks; c += NT) {
+        const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
+        const int valid = (int)len - (int)(16 * c);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t x = cw.w[k + 2], u = uw.w[k + 2], l = left_word<D>(cw, k, shift), ul = left_word<D>(uw, k, shift);
+            const int nv = valid - 4 * k;
+            if (nv <= 0) break;
+            hist_add4(h + 0 * HIST_REP * 256, x, nv);
+            hist_add4(h + 1 * HIST_REP * 256, __vsub4(x, l), nv);
+            hist_add4(h + 2 * HIST_REP * 256, __vsub4(x, u), nv);
+            hist_add4(h + 3 * HIST_REP * 256, __vsub4(x, __vhaddu4(l, u)), nv);
+            hist_add4(h + 4 * HIST_REP * 256, __vsub4(x, paeth4(l, u, ul)), nv);
+        }
+    }
+}
+// sum over present values of ilog2i(count) (strategies.rs:136-142); clears the histograms for the next row.
+template <int NT>
+__device__ __forceinline__ void entropy_score(uint32_t *hist, uint32_t *s_ent) {
+    for (uint32_t idx = threadIdx.x; idx < 5 * 256; idx += NT) {
+        const uint32_t f = idx >> 8, v = idx & 255u;
+        uint32_t *h = hist + f * HIST_REP * 256 + v;
+        uint32_t cnt = (v == f) ? 1u : 0u; // the filter-type byte that leads the filtered line
+#pragma unroll
+        for (int r = 0; r < HIST_REP; r++) {
+            cnt += h[r * 256];
+            h[r * 256] = 0;
+        }
+        uint32_t s = warp_sum(cnt ? ilog2i(cnt) : 0u);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_ent[f], s);
+    }
+}
+
+// One Bigrams/BigEnt trial for filter F over the stream t[0]=F, t[1+i]=residual[i]: windows (t[p-1], t[p]), p=1..len.
+// Pass 1 counts into the u16 table (the adder that sees 0 owns the bigram); pass 2 lets owners read the final count,
+// contribute 1 to the distinct count and ilog2i(count) to the entropy, and clear the entry.
+template <int D, int NT, int F>
+__device__ __forceinline__ void bigram_trial(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
+                                             uint32_t *table, uint32_t *s_bgc, uint32_t *s_bge) {
+    const uint32_t nchunks = (len + 15) >> 4;
+    unsigned long long own = 0;
+    uint16_t *t16 = reinterpret_cast<uint16_t *>(table);
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        int bit = 0;
+        uint32_t distinct = 0, ent = 0;
+        for (uint32_t c = threadIdx.x; c < nchunks; c += NT) {
+            const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
+            const int valid = (int)len - (int)(16 * c);
+            // byte of the stream just before this chunk: the filter id for chunk 0, else the previous residual
+            uint32_t prev = c == 0 ? (uint32_t)F : residual_at(F, cur, up, (int)(16 * c) - 1, bpp);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t x = cw.w[k + 2];
+                const uint32_t r = __vsub4(x, pred4<F>(left_word<D>(cw, k, shift), uw.w[k + 2], left_word<D>(uw, k, shift)));
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t b = (r >> (8 * j)) & 255u;
+                    const uint32_t bg = (prev << 8) | b;
+                    prev = b;
+                    if (4 * k + j < valid) {
+                        if (pass == 0) {
+                            const uint32_t old = atomicAdd(&table[bg >> 1], (bg & 1u) ? 0x10000u : 1u);
+                            const uint32_t cnt = (bg & 1u) ? (old >> 16) : (old & 0xFFFFu);
+                            if (cnt == 0) own |= 1ull << bit;
+                        } else if ((own >> bit) & 1ull) {
+                            const uint32_t cnt = t16[bg];
+                            t16[bg] = 0;
+                            distinct += 1;
+                            ent += ilog2i(cnt);
+                        }
+                    }
+                    bit++;
+                }
+            }
+        }
+        if (pass == 1) {
+            distinct = warp_sum(distinct);
+            ent = warp_sum(ent);
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(&s_bgc[F], distinct);
+                atomicAdd(&s_bge[F], ent);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- writing the chosen row --------------------------------------------------------------------------------------
+// out_row points at the filter-type byte of this row in the filtered stream.  Interior 16-byte granules of the
+// output are produced in the output's alignment frame; the (at most 31) edge bytes are written one by one.
+template <int NT>
+__device__ __forceinline__ void write_row(int f, const uint8_t *cur, const uint8_t *up, uint32_t len, int bpp,
+                                          uint8_t *out_row) {
+    const int phase = (int)(reinterpret_cast<uintptr_t>(out_row) & 15u);
+    const int total = (int)len + 1;                 // stream positions p = 0..len
+    const int q_full_end = (total + phase) >> 4;    // granules [1, q_full_end) are complete and hold residuals only
+    uint8_t *base = out_row - phase;
+    for (int q = 1 + (int)threadIdx.x; q < q_full_end; q += NT) {
+        const int i0 = 16 * q - phase - 1; // row byte of the granule's first position (>= 0)
+        const uint4 x = ld_unaligned16(cur + i0);
+        uint4 r;
+        if (f == 0) {
+            r = x;
+        } else if (f == 1) {
+            const uint4 l = ld_unaligned16(cur + i0 - bpp);
+            r.x = __vsub4(x.x, l.x); r.y = __vsub4(x.y, l.y); r.z = __vsub4(x.z, l.z); r.w = __vsub4(x.w, l.w);
+        } else if (f == 2) {
+            const uint4 u = ld_unaligned16(up + i0);
+            r.x = __vsub4(x.x, u.x); r.y = __vsub4(x.y, u.y); r.z = __vsub4(x.z, u.z); r.w = __vsub4(x.w, u.w);
+        } else if (f == 3) {
+            const uint4 l = ld_unaligned16(cur + i0 - bpp), u = ld_unaligned16(up + i0);
+            r.x = __vsub4(x.x, __vhaddu4(l.x, u.x)); r.y = __vsub4(x.y, __vhaddu4(l.y, u.y));
+            r.z = __vsub4(x.z, __vhaddu4(l.z, u.z)); r.w = __vsub4(x.w, __vhaddu4(l.w, u.w));
+        } else {
+            const uint4 l = ld_unaligned16(cur + i0 - bpp), u = ld_unaligned16(up + i0), ul = ld_unaligned16(up + i0 - bpp);
+            r.x = __vsub4(x.x, paeth4(l.x, u.x, ul.x)); r.y = __vsub4(x.y, paeth4(l.y, u.y, ul.y));
+            r.z = __vsub4(x.z, paeth4(l.z, u.z, ul.z)); r.w = __vsub4(x.w, paeth4(l.w, u.w, ul.w));
+        }
+        __stcs(reinterpret_cast<uint4 *>(base + 16 * (size_t)q), r);
+    }
+    // edges: positions [0, head_end) of granule 0 and [tail_begin, total) of the last, partial granule
+    const int head_end = min(16 - phase, total);
+    const int tail_begin = max(16 * q_full_end - phase, head_end);
+    const int n_edge = head_end + (total - tail_begin);
+    for (int e = threadIdx.x; e < n_edge; e += NT) {
+        const int p = e < head_end ? e : tail_begin + (e - head_end);
+        out_row[p] = p == 0 ? (uint8_t)f : (uint8_t)residual_at(f, cur, up, p - 1, bpp);
+    }
+}
+
+// cooperative, alignment-agnostic row load (rows that TMA cannot take: not 16-byte aligned / sized)
+template <int NT>
+__device__ __forceinline__ void coop_load_row(uint8_t *dst, const uint8_t *src, uint32_t len) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t *g = reinterpret_cast<const uint32_t *>(src - mis);
+    const uint32_t nsrc = (len + mis + 3) >> 2, ndst = (len + 3) >> 2, s = 8 * mis;
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst);
+    for (uint32_t k = threadIdx.x; k < ndst; k += NT) {
+        const uint32_t lo = __ldg(g + k);
+        const uint32_t hi = (mis && k + 1 < nsrc) ? __ldg(g + k + 1) : 0u;
+        d[k] = __funnelshift_r(lo, hi, s);
+    }
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------------------
+template <int D, int SC>
+__global__ void __launch_bounds__(threads_for(SC), 1) k_fast(const __grid_constant__ FastParams P) {
+    constexpr int NT = threads_for(SC);
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const Smem sm = carve<SC>(smem_raw, P.rb);
+    const int tid = threadIdx.x;
+    const int bpp = (int)P.g.bpp;
+    const uint32_t shift = P.shift;
+
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_init(&sm.bar[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) sm.s_min[tid] = 0;
+    for (uint32_t i = tid; i < 3 * PAD / 4; i += NT) // zero the left pad of each slot (never written again)
+        reinterpret_cast<uint32_t *>(sm.rows + (i / (PAD / 4)) * (size_t)P.rb)[i % (PAD / 4)] = 0;
+    if (SC & SC_ENTROPY)
+        for (uint32_t i = tid; i < 5 * HIST_REP * 256; i += NT) sm.hist[i] = 0;
+    if (SC & SC_BIGRAM)
+        for (uint32_t i = tid; i < 32768; i += NT) sm.table[i] = 0;
+    __syncthreads();
+
+    uint32_t parity = 0; // bit s = phase to wait for on slot s
+    const uint64_t total_items = P.n_images * (uint64_t)P.items_per_image;
+    bool any_heur = false;
+    for (int j = 0; j < P.set.k; j++) any_heur |= (P.set.s[j].kind != OXI_BASIC && P.set.s[j].kind != OXI_PREDEFINED);
+
+    for (uint64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const uint64_t img = item / P.items_per_image;
+        const uint32_t it = (uint32_t)(item % P.items_per_image);
+        int p = 0;
+#pragma unroll
+        for (int i = 1; i < 7; i++)
+            if (i < (int)P.g.n_pass && it >= P.band_start[i]) p = i;
+        const PassDesc pd = P.g.pass[p];
+        const uint32_t nb = P.band_start[p + 1] - P.band_start[p], b = it - P.band_start[p];
+        const uint32_t k0 = (uint32_t)(((uint64_t)b * pd.nrows) / nb), k1 = (uint32_t)(((uint64_t)(b + 1) * pd.nrows) / nb);
+        if (k0 >= k1) continue;
+        const uint32_t len = pd.len;
+        const uint8_t *src0 = P.data + img * P.g.data_len + pd.in_base; // first row of the pass
+        const bool tma = ((reinterpret_cast<uintptr_t>(src0) | len) & 15u) == 0;
+
+        // prologue: previous row (or zeros at a pass start, png/mod.rs:375-378) into slot 0, first row into slot 1
+        if (k0 == 0) {
+            uint4 *z = reinterpret_cast<uint4 *>(sm.rows + PAD);
+            for (uint32_t i = tid; i < (len + 15) / 16; i += NT) z[i] = make_uint4(0, 0, 0, 0);
+            fence_proxy_async();
+        }
+        if (tma) {
+            if (tid == 0) {
+                if (k0 > 0) {
+                    mbar_expect_tx(&sm.bar[0], len);
+                    tma_load_1d(sm.rows + PAD, src0 + (size_t)(k0 - 1) * len, len, &sm.bar[0]);
+                }
+                mbar_expect_tx(&sm.bar[1], len);
+                tma_load_1d(sm.rows + P.rb + PAD, src0 + (size_t)k0 * len, len, &sm.bar[1]);
+            }
+            if (k0 > 0) {
+                mbar_wait(&sm.bar[0], parity & 1u);
+                parity ^= 1u;
+            }
+        } else {
+            if (k0 > 0) coop_load_row<NT>(sm.rows + PAD, src0 + (size_t)(k0 - 1) * len, len);
+            coop_load_row<NT>(sm.rows + P.rb + PAD, src0 + (size_t)k0 * len, len);
+        }
+        __syncthreads();
+
+        for (uint32_t k = k0; k < k1; k++) {
+            const uint32_t j = k - k0 + 1, sc_ = j % 3, sp = (j + 2) % 3, sn = (j + 1) % 3;
+            const uint8_t *cur = sm.rows + sc_ * (size_t)P.rb + PAD;
+            const uint8_t *up = sm.rows + sp * (size_t)P.rb + PAD;
+            if (k + 1 < k1) { // stream the next row in behind the current one
+                uint8_t *dst = sm.rows + sn * (size_t)P.rb + PAD;
+                if (tma) {
+                    if (tid == 0) {
+                        mbar_expect_tx(&sm.bar[sn], len);
+                        tma_load_1d(dst, src0 + (size_t)(k + 1) * len, len, &sm.bar[sn]);
+                    }
+                } else {
+                    coop_load_row<NT>(dst, src0 + (size_t)(k + 1) * len, len);
+                }
+            }
+            if (tma) {
+                mbar_wait(&sm.bar[sc_], (parity >> sc_) & 1u);
+                parity ^= 1u << sc_;
+            }
+
+            const uint32_t r = pd.row0 + k;
+            const uint64_t in_off = pd.in_base + (uint64_t)k * len;
+            bool heur = false;
+            if (SC != 0 && any_heur) {
+                // all-zero rows short-circuit to None (png/mod.rs:398-404)
+                uint32_t nz = 0;
+                const uint4 *c4 = reinterpret_cast<const uint4 *>(cur);
+                const uint32_t nchunks = (len + 15) >> 4;
+                for (uint32_t c = tid; c < nchunks; c += NT) {
+                    uint4 v = c4[c];
+                    const int valid = (int)len - (int)(16 * c);
+                    if (valid < 16) {
+                        v.x &= tail_mask(valid); v.y &= tail_mask(valid - 4); v.z &= tail_mask(valid - 8);
+                        v.w &= tail_mask(valid - 12);
+                    }
+                    nz |= v.x | v.y | v.z | v.w;
+                }
+                if (tid < 32) sm.s_min[tid] = 0; // clears s_min, s_ent, s_bgc, s_bge
+                heur = __syncthreads_or(nz != 0) != 0;
+                if (heur) {
+                    if (SC & SC_MINSUM) minsum_pass<D, NT>(cur, up, len, shift, sm.s_min);
+                    if (SC & SC_ENTROPY) {
+                        entropy_pass<D, NT>(cur, up, len, shift, sm.hist);
+                        __syncthreads();
+                        entropy_score<NT>(sm.hist, sm.s_ent);
+                    }
+                    if (SC & SC_BIGRAM) {
+                        bigram_trial<D, NT, 0>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
+                        bigram_trial<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
+                        bigram_trial<D, NT, 2>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
+                        bigram_trial<D, NT, 3>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
+                        bigram_trial<D, NT, 4>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
+                    }
+                    __syncthreads();
+                }
+            }
+
+            for (int j2 = 0; j2 < P.set.k; j2++) {
+                const DevStrategy &st = P.set.s[j2];
+                int f = 0;
+                if (st.kind == OXI_BASIC) {
+                    f = st.basic;
+                } else if (st.kind == OXI_PREDEFINED) {
+                    f = r < st.n_predefined ? st.predefined[r] : 0; // png/mod.rs:389
+                } else if (heur) {
+                    if (st.kind == OXI_MINSUM) { // smaller is better, strict '<' (strategies.rs:95)
+                        uint32_t best = 0xFFFFFFFFu;
+                        const uint32_t nbytes = 16 * ((len + 15) >> 4);
+#pragma unroll
+                        for (int q = 0; q < 5; q++) {
+                            const uint32_t s = 128u * nbytes - sm.s_min[q] + (uint32_t)q;
+                            if (s < best || q == 0) { best = s; f = q; }
+                        }
+                    } else if (st.kind == OXI_BIGRAMS) { // fewer distinct bigrams, strict '<' (strategies.rs:182-189)
+                        uint32_t best = 0;
+#pragma unroll
+                        for (int q = 0; q < 5; q++) {
+                            const uint32_t s = sm.s_bgc[q];
+                            if (q == 0 || s < best) { best = s; f = q; }
+                        }
+                    } else { // Entropy / BigEnt: larger is better, strict '>' on i32 (strategies.rs:143,221)
+                        const uint32_t *sc = st.kind == OXI_ENTROPY ? sm.s_ent : sm.s_bge;
+                        int32_t best = 0;
+#pragma unroll
+                        for (int q = 0; q < 5; q++) {
+                            const int32_t s = (int32_t)sc[q];
+                            if (q == 0 || s > best) { best = s; f = q; }
+                        }
+                    }
+                }
+                write_row<NT>(f, cur, up, len, bpp, st.out + img * P.g.out_len + in_off + r);
+                if (tid == 0) st.filters_used[img * P.g.total_rows + r] = (uint8_t)f;
+            }
+            __syncthreads(); // slot `sp` may be refilled by the next iteration's prefetch
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+
+int scorers_needed(const StrategySet &set) {
+    int sc = 0;
+    for (int j = 0; j < set.k; j++) {
+        switch (set.s[j].kind) {
+        case OXI_MINSUM: sc |= SC_MINSUM; break;
+        case OXI_ENTROPY: sc |= SC_ENTROPY; break;
+        case OXI_BIGRAMS: case OXI_BIGENT: sc |= SC_BIGRAM; break;
+        default: break;
+        }
+    }
+    return sc;
+}
+// Kernels are instantiated for the scorer sets that occur in practice; any other mixture runs the full kernel.
+int kernel_sc(int sc) {
+    if (sc == 0 || sc == SC_MINSUM || sc == SC_ENTROPY || sc == SC_BIGRAM) return sc;
+    return SC_MINSUM | SC_ENTROPY | SC_BIGRAM;
+}
+uint32_t slot_bytes(const Geom &g) { return PAD + ((g.max_len + 15u) & ~15u) + PAD; }
+
+using KernelFn = void (*)(const FastParams);
+template <int D>
+KernelFn pick_sc(int sc) {
+    switch (sc) {
+    case 0: return k_fast<D, 0>;
+    case SC_MINSUM: return k_fast<D, SC_MINSUM>;
+    case SC_ENTROPY: return k_fast<D, SC_ENTROPY>;
+    case SC_BIGRAM: return k_fast<D, SC_BIGRAM>;
+    default: return k_fast<D, SC_MINSUM | SC_ENTROPY | SC_BIGRAM>;
+    }
+}
+KernelFn pick_kernel(int d, int sc) { return d == 0 ? pick_sc<0>(sc) : d == 1 ? pick_sc<1>(sc) : pick_sc<2>(sc); }
+
+std::mutex g_occ_mu;
+std::map<std::pair<const void *, uint32_t>, int> g_occ; // (kernel, smem) -> resident CTAs per SM
+
+} // namespace
+
+bool fast_supported(const Geom &g, const StrategySet &set) {
+    if (g.alpha_bytes != 0 || g.total_rows == 0) return false;
+    if (g.bpp != 1 && g.bpp != 2 && g.bpp != 3 && g.bpp != 4 && g.bpp != 6 && g.bpp != 8) return false;
+    const int sc = kernel_sc(scorers_needed(set));
+    if (smem_bytes_for(sc, slot_bytes(g)) > SMEM_LIMIT) return false;
+    if ((sc & SC_BIGRAM) && g.max_len > 65535u) return false; // u16 counters and the 64-bit owner mask
+    return true;
+}
+
+cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_data, size_t n_images,
+                        const StrategySet &set) {
+    const int sc = kernel_sc(scorers_needed(set));
+    const int nt = threads_for(sc);
+    FastParams P;
+    P.g = g;
+    P.set = set;
+    P.data = d_data;
+    P.n_images = n_images;
+    P.rb = slot_bytes(g);
+    P.shift = 8 * (g.bpp % 4);
+    const uint32_t smem = smem_bytes_for(sc, P.rb);
+    KernelFn fn = pick_kernel((int)(g.bpp / 4), sc);
+    cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_occ_mu);
+        auto key = std::make_pair((const void *)fn, smem + (uint32_t)ctx.device * 0x1000000u);
+        auto it = g_occ.find(key);
+        if (it == g_occ.end()) {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, nt, smem);
+            if (e != cudaSuccess) return e;
+            if (occ < 1) occ = 1;
+            g_occ[key] = occ;
+        } else {
+            occ = it->second;
+        }
+    }
+    // Bands: enough work items to fill every resident CTA slot a few times over, but not so many that the one-row
+    // halo per band becomes a large share of the reads.  Bands never cross a pass (png/mod.rs:375-378).
+    const uint64_t slots = (uint64_t)ctx.num_sms * occ;
+    const uint64_t want_items = slots * 4;
+    uint64_t per_image = (want_items + n_images - 1) / n_images;
+    if (per_image < 1) per_image = 1;
+    uint32_t acc = 0;
+    for (uint32_t p = 0; p < 7; p++) {
+        P.band_start[p] = acc;
+        if (p < g.n_pass) {
+            const uint64_t bytes = (uint64_t)g.pass[p].nrows * g.pass[p].len;
+            uint64_t nb = (per_image * bytes + g.data_len - 1) / (g.data_len ? g.data_len : 1);
+            const uint64_t max_nb = (g.pass[p].nrows + 3) / 4; // keep >= 4 rows per band when possible
+            if (nb > max_nb) nb = max_nb;
+            if (nb < 1) nb = 1;
+            acc += (uint32_t)nb;
+        }
+    }
+    P.band_start[7] = acc;
+    for (uint32_t p = g.n_pass; p < 7; p++) P.band_start[p] = acc;
+    P.items_per_image = acc;
+    const uint64_t items = (uint64_t)acc * n_images;
+    uint64_t grid = items < slots ? items : slots;
+    if (grid < 1) grid = 1;
+    fn<<<(unsigned)grid, nt, smem, ctx.stream>>>(P);
+    count_launch();
+    return cudaGetLastError();
+}
+
 } // namespace oxi
