@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- filter-search throughput of the B200 path on BASELINE.json's batch configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--images-per-gpu B] [--others]
+
+Workload (config c5 of BASELINE.json): a batch of synthetic 1024x1024 RGBA8 images filtered with the -o4 strategy
+set that stays on the GPU, {None, Bigrams, BigEnt} (src/options.rs:220-233; Brute stays on the host), sharded by
+image across GPUs with no data-path collective.  Weak scaling: 1250 images per GPU, i.e. the named 10 000-image
+batch at 8 GPUs.  A step = one fused 3-strategy pass over the rank's whole batch.
+
+  value      raw-pixel GB/s, whole job, inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e        the same through the host-buffer C-ABI call oxi_filter_batch (pinned host memory, H2D + D2H inside)
+  roofline   algorithmic bytes of the dominant kernel / its event-timed duration vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference   the CPU oracle (restated reference, "port": the Rust reference cannot be built
+             here) on all host threads over a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMG_W = IMG_H = 1024
+CHANNELS = 4
+PER_IMAGE = IMG_W * IMG_H * CHANNELS      # N = 4 194 304 raw bytes
+ROWS = IMG_H                              # S
+SEED0 = 0xB2000005
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on all host threads (bench.py may execute oracle/ only here)
+# ---------------------------------------------------------------------------------------------------------------
+
+def cpu_filter_throughput(images, threads: int):
+    """images: list of numpy arrays (one 1024x1024 RGBA8 image each). Runs {None,Bigrams,BigEnt} on each with a
+    thread pool (ctypes releases the GIL), mirroring rayon's fan-out over (image x strategy) (evaluate.rs:143).
+    -> seconds"""
+    import concurrent.futures as cf
+    import oracle
+    ih = (IMG_W, IMG_H, 6, 8, 0)
+    tasks = [(d, k) for d in images for k in ((oracle.BASIC), (oracle.BIGRAMS), (oracle.BIGENT))]
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(lambda t: oracle.filter_image(ih, t[0], t[1], 0), tasks))
+    return time.perf_counter() - t0
+
+
+def host_images(n: int):
+    import torch
+    from oxipng_b200 import synth
+    return [synth.photo_image(IMG_W, IMG_H, CHANNELS, 8, SEED0 + i, "cpu").numpy() for i in range(n)]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.use_native()
+    threads = os.cpu_count() or 1
+    n = max(threads, 8)  # bounded sample: one image per host thread and step (x3 strategies)
+    imgs = host_images(n)
+    for _ in range(args.warmup):
+        cpu_filter_throughput(imgs[:max(threads // 2, 1)], threads)
+    times = [cpu_filter_throughput(imgs, threads) for _ in range(args.steps)]
+    sec = sum(times) / len(times)
+    gbs = n * PER_IMAGE / sec / 1e9
+    line = {
+        "impl": "reference", "metric": "filter_search_raw_pixel_throughput", "value": gbs, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, n),
+        "images_per_s": n / sec,
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} images x {{None,Bigrams,BigEnt}} per step, {threads} threads, "
+                                   "C restatement of the reference (oracle/), gcc -O3 -march=native"},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, images_this_step=None):
+    return {"workload": "c5: batch of 1024x1024 RGBA8 synthetic images, strategies {None,Bigrams,BigEnt} "
+                        "(-o4 set without Brute), sharded by image",
+            "images_per_gpu": args.images_per_gpu, "image": "1024x1024 RGBA8 (4 194 304 B, 1024 scanlines)",
+            "strategies": ["None", "Bigrams", "BigEnt"], "optimize_alpha": False,
+            "l2": "per-GPU input 5.2 GB and output 15.7 GB >> 126 MB L2; no flush needed",
+            "images_in_step": images_this_step}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML)
+# ---------------------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            log("clock sampler unavailable:", e)
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv:
+            self._stop.clear()
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t:
+            self._stop.set()
+            self._t.join()
+            self._t = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def time_device(fn, steps, warmup, stream, dist, torch):
+    """-> (total ms over `steps`, [per-launch ms]) timed with CUDA events on `stream`, barrier + sync on both sides"""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record(stream)
+    for i in range(steps):
+        fn()
+        evs[i + 1].record(stream)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    return evs[0].elapsed_time(evs[steps]), per
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import oxipng_b200 as ox
+    from oxipng_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+    L = ox.lib()
+    from oxipng_b200._lib import check
+    check(L.oxi_set_device(local), "oxi_set_device")
+
+    B = args.images_per_gpu
+    hdr = ox.IhdrData(IMG_W, IMG_H, ox.ColorType.RGBA(), ox.BitDepth.Eight, False)
+    strategies = [ox.FilterStrategy.NONE, ox.FilterStrategy.Bigrams, ox.FilterStrategy.BigEnt]
+    K = len(strategies)
+    out_per = PER_IMAGE + ROWS
+    log(f"[rank {rank}] generating {B} images on {dev} ...")
+    t0 = time.perf_counter()
+    d_in = synth.photo_batch(B, IMG_W, IMG_H, CHANNELS, 8, SEED0 + rank * B, dev)
+    d_out = [torch.empty(B * out_per, dtype=torch.uint8, device=dev) for _ in range(K)]
+    d_used = [torch.empty(B * ROWS, dtype=torch.uint8, device=dev) for _ in range(K)]
+    torch.cuda.synchronize()
+    log(f"[rank {rank}] generated in {time.perf_counter() - t0:.1f}s")
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        ox.filter_batch_device(local, stream.cuda_stream, hdr, d_in.data_ptr(), PER_IMAGE, B, strategies, False,
+                               [t.data_ptr() for t in d_out], [t.data_ptr() for t in d_used])
+
+    # --- correctness spot check against the oracle (checker only) on rank 0: first and last image
+    if rank == 0 and not args.no_check:
+        import oracle
+        step()
+        torch.cuda.synchronize()
+        for i in (0, B - 1):
+            img = d_in[i * PER_IMAGE:(i + 1) * PER_IMAGE].cpu().numpy()
+            for j, kind in enumerate((oracle.BASIC, oracle.BIGRAMS, oracle.BIGENT)):
+                want, used, _ = oracle.filter_image((IMG_W, IMG_H, 6, 8, 0), img, kind, 0)
+                got = d_out[j][i * out_per:(i + 1) * out_per].cpu().numpy()
+                gu = d_used[j][i * ROWS:(i + 1) * ROWS].cpu().numpy()
+                if not (np.array_equal(got, want) and np.array_equal(gu, used)):
+                    raise SystemExit(f"parity check failed: image {i} strategy {j}")
+        log("[rank 0] parity spot check vs oracle: ok")
+
+    # --- device-resident timing (value, roofline)
+    sampler = ClockSampler(local)
+    launches0 = L.oxi_kernel_launches()
+    sampler.start()
+    total_ms, per_launch = time_device(step, args.steps, args.warmup, stream, dist, torch)
+    sampler.stop()
+    launches = L.oxi_kernel_launches() - launches0 - args.warmup
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    images_total = B * world
+    value = images_total * PER_IMAGE / (ms_per_step * 1e-3) / 1e9
+
+    # roofline of the dominant (only) kernel: k_fast<D=1, SC_BIGRAM>, one launch per step
+    alg_bytes = B * (PER_IMAGE + K * (PER_IMAGE + 2 * ROWS))  # N + K(N+2S) per image, SURVEY 8d
+    avg_launch_ms = sum(per_launch) / len(per_launch)
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("c5_bytes_per_launch_at_bench_batch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "k_fast<D=1,SC_BIGRAM> (fused None+Bigrams+BigEnt)",
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_launch_ms, "peak_source": peak_src,
+                "limiter": "shared-memory atomics (bigram counter table), not HBM"}
+
+    # --- end to end through the host-buffer C-ABI call (pinned host memory; H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        Be = B
+        h_in = torch.empty(Be * PER_IMAGE, dtype=torch.uint8, pin_memory=True)
+        h_in.copy_(d_in[:Be * PER_IMAGE])
+        h_out = [torch.empty(Be * out_per, dtype=torch.uint8, pin_memory=True) for _ in range(K)]
+        h_used = [torch.empty(Be * ROWS, dtype=torch.uint8, pin_memory=True) for _ in range(K)]
+        np_in = h_in.numpy()
+        np_out = [t.numpy() for t in h_out]
+        np_used = [t.numpy() for t in h_used]
+
+        def e2e_step():
+            ox.filter_batch(hdr, np_in, Be, strategies, False, 0, np_out, np_used)
+
+        for _ in range(max(args.warmup, 1)):
+            e2e_step()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        sampler.start()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        sampler.stop()
+        te = torch.tensor([el], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        el = float(te.item())
+        e2e = {"value": Be * world * PER_IMAGE * args.steps / el / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": Be * PER_IMAGE, "d2h_bytes_per_step": Be * K * (out_per + ROWS),
+               "ms_per_step": el / args.steps * 1e3, "images_per_s": Be * world * args.steps / el,
+               "api": "oxi_filter_batch (host buffers, pinned; chunked H2D/kernel/D2H pipeline)"}
+        del h_in, h_out, h_used
+
+    # --- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle
+        oracle.use_native()
+        threads = os.cpu_count() or 1
+        n = max(threads, 8)
+        imgs = [d_in[i * PER_IMAGE:(i + 1) * PER_IMAGE].cpu().numpy() for i in range(n)]
+        cpu_filter_throughput(imgs[:max(threads // 2, 1)], threads)
+        reps, t_acc = 0, 0.0
+        while t_acc < 10.0 and reps < 8:
+            t_acc += cpu_filter_throughput(imgs, threads)
+            reps += 1
+        cpu = {"value": n * reps * PER_IMAGE / t_acc / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+               "sample": f"{n} images x {{None,Bigrams,BigEnt}} x {reps} reps ({t_acc:.1f}s), {threads} threads, "
+                         "C restatement of the reference (oracle/), gcc -O3 -march=native; "
+                         "the Rust reference cannot be built in this image"}
+
+    others = None
+    if args.others and rank == 0:
+        others = run_other_configs(ox, synth, torch, dev, local, stream, args)
+
+    if rank == 0:
+        line = {
+            "metric": "filter_search_raw_pixel_throughput", "value": value, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, images_total),
+            "images_per_s": images_total / (ms_per_step * 1e-3),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+        if others is not None:
+            line["other_configs"] = others
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_other_configs(ox, synth, torch, dev, local, stream, args):
+    """Kernel-only throughput of the single-image BASELINE configs c1-c3 (device-resident, L2 flushed between
+    iterations because these inputs are smaller than the 126 MB L2)."""
+    peak, _ = peaks()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    res = {}
+    cfgs = [
+        ("c1_minsum_rgba8_4096", 4096, 4096, 4, 8, False, [ox.FilterStrategy.MinSum]),
+        ("c2_entropy_rgb8_8192", 8192, 8192, 3, 8, False, [ox.FilterStrategy.Entropy]),
+        ("c2_basic_paeth_rgb8_8192", 8192, 8192, 3, 8, False, [ox.FilterStrategy.PAETH]),
+        ("c2_basic_none_rgb8_8192", 8192, 8192, 3, 8, False, [ox.FilterStrategy.NONE]),
+        ("c3a_bigrams_rgba16_4096", 4096, 4096, 4, 16, False, [ox.FilterStrategy.Bigrams]),
+        ("c3a_bigent_rgba16_4096", 4096, 4096, 4, 16, False, [ox.FilterStrategy.BigEnt]),
+    ]
+    for name, w, h, ch, bd, il, strat in cfgs:
+        ct = {1: ox.ColorType.Grayscale(), 3: ox.ColorType.RGB(), 4: ox.ColorType.RGBA()}[ch]
+        hdr = ox.IhdrData(w, h, ct, ox.BitDepth(bd), il)
+        d = synth.photo_image(w, h, ch, bd, 0xB2000001, dev)
+        n, rows = d.numel(), h
+        o = [torch.empty(n + rows, dtype=torch.uint8, device=dev) for _ in strat]
+        u = [torch.empty(rows, dtype=torch.uint8, device=dev) for _ in strat]
+
+        def step():
+            ox.filter_batch_device(local, stream.cuda_stream, hdr, d.data_ptr(), n, 1, strat, False,
+                                   [t.data_ptr() for t in o], [t.data_ptr() for t in u])
+        for _ in range(3):
+            step()
+        times = []
+        for _ in range(max(args.steps, 5)):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = statistics.median(times)
+        alg = n + len(strat) * (n + 2 * rows)
+        res[name] = {"ms": ms, "raw_pixel_GBps": n / ms / 1e6, "algorithmic_GBps": alg / ms / 1e6,
+                     "frac_of_measured_hbm": alg / ms / 1e6 / peak, "l2": "flushed (512 MB fill) between iterations"}
+        del d, o, u
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images-per-gpu", type=int, default=1250)
+    ap.add_argument("--others", action="store_true", help="also time the single-image configs c1-c3 (kernel only)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -320,3 +320,26 @@ def apply_palette_reorder(ihdr, data, palette, remapping):
     rc = lib().oxo_apply_palette_reorder(C.byref(h), C.byref(a), _p(rm), _p(d), C.c_size_t(d.size), _p(out),
                                          C.byref(oa))
     return None if rc else _res(h, out[:d.size].copy(), oa)
+
+
+def use_native() -> bool:
+    """For CPU-baseline timing only: rebuild the oracle with -march=native on this host (if gcc is present) and switch
+    the binding to it.  Returns True when the native build is in use."""
+    global _lib
+    native = os.path.join(_HERE, "liboxi_oracle_native.so")
+    try:
+        src = os.path.join(_HERE, "oxi_oracle.c")
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-std=c11", "-shared", "-o", native, src, "-lm"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        return False
+    saved = globals().get("_LIB_PATH")
+    try:
+        globals()["_LIB_PATH"] = native
+        _lib = None
+        lib()
+        return True
+    except Exception:
+        globals()["_LIB_PATH"] = saved
+        _lib = None
+        return False

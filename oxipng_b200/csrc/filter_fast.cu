@@ -68,7 +68,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- byte-SIMD helpers ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t signmask4(uint32_t x) { return __byte_perm(x, 0, 0xba98); } // 0xFF where MSB set
+__device__ __forceinline__ uint32_t signmask4(uint32_t x) { // 0xFF in every byte whose MSB is set
+    uint32_t d;                                             // (prmt's sign-replicate selectors; __byte_perm masks them off)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xba98u));
+    return d;
+}
 __device__ __forceinline__ uint32_t sel4(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
 
 // paeth_predictor (src/filters/mod.rs:242-254) on four byte lanes, without widening.

@@ -123,3 +123,51 @@ def test_device_resident_api_matches_host_api():
     for j in range(len(strat)):
         assert np.array_equal(t_out[j].cpu().numpy(), want_o[j])
         assert np.array_equal(t_used[j].cpu().numpy(), want_u[j])
+
+
+def test_fast_tier_covers_benchmark_shapes():
+    """The fast (TMA-staged) tier, forced, on scaled-down versions of every BASELINE config incl. rows that are and are
+    not 16-byte multiples, every filter bpp (1,2,3,4,6,8) and interlaced passes."""
+    import oxipng_b200 as ox
+    shapes = [
+        (1024, 40, 6, 8, False, "photo"),     # C1/C5: RGBA8, TMA-aligned rows
+        (2048, 24, 2, 8, False, "photo"),     # C2: RGB8
+        (512, 32, 6, 16, False, "photo"),     # C3a: RGBA16 (bpp 8)
+        (512, 64, 6, 8, True, "photo"),       # C3b: Adam7 RGBA8
+        (500, 33, 2, 8, False, "photo"),      # reference fixture geometry: 1500-byte rows, no TMA
+        (333, 17, 4, 8, False, "random"),     # bpp 2, odd
+        (257, 19, 2, 16, True, "random"),     # bpp 6 interlaced
+        (1000, 9, 0, 8, False, "photo"),      # bpp 1
+        (999, 21, 0, 4, False, "random"),     # packed 4-bit
+        (640, 16, 3, 1, True, "random"),      # packed 1-bit interlaced
+        (256, 20, 6, 8, False, "flat"),       # heavy ties / hot histogram bins
+        (256, 20, 6, 8, False, "zeros"),      # all-zero shortcut
+        (4096, 6, 6, 16, False, "random"),    # 32 KB rows: largest bigram-table configuration
+    ]
+    for (w, h, ct, bd, il, kind) in shapes:
+        ih, d = helpers.synth_image(w, h, ct, bd, 4242 + w, kind, il)
+        img = helpers.product_image(ih, d)
+        assert ox.filter_tier(img, ox.FilterStrategy.BigEnt, False) == "fast", (w, h, ct, bd)
+        # one strategy per launch (specialised kernels) ...
+        for n in [s[0] for s in helpers.STRATEGIES]:
+            _check(ih, d, alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=[n], label=f"fast1/{w}x{h}/{ct}/{bd}/{il}/{kind}")
+        # ... and the fused multi-strategy launch (evaluate.rs fan-out)
+        # (all scorers resident at once need 3 rows + 148 KB of tables: 32 KB rows fall back to the generic tier)
+        fused_flags = ox.FLAG_FORCE_FAST if helpers.row_bytes(ih) <= 16384 else 0
+        _check(ih, d, alphas=(False,), flags=fused_flags, label=f"fastN/{w}x{h}/{ct}/{bd}/{il}/{kind}")
+        _check(ih, d, alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["None", "Bigrams", "BigEnt"], label="o4")
+
+
+def test_fast_tier_batch_many_images():
+    import oxipng_b200 as ox
+    n = 37
+    imgs = [helpers.synth_image(256, 48, 6, 8, 900 + i, "photo" if i % 3 else "random") for i in range(n)]
+    ih = imgs[0][0]
+    hdr = helpers.product_image(ih, imgs[0][1]).ihdr
+    data = np.concatenate([d for _, d in imgs])
+    strat = [ox.FilterStrategy.NONE, ox.FilterStrategy.Bigrams, ox.FilterStrategy.BigEnt]
+    outs, used = ox.filter_batch(hdr, data, n, strat, False, ox.FLAG_FORCE_FAST)
+    for j, (kind, basic) in enumerate([(oracle.BASIC, 0), (oracle.BIGRAMS, 0), (oracle.BIGENT, 0)]):
+        want = [oracle.filter_image(ih, d, kind, basic) for _, d in imgs]
+        assert np.array_equal(used[j], np.concatenate([w[1] for w in want])), j
+        assert np.array_equal(outs[j], np.concatenate([w[0] for w in want])), j
