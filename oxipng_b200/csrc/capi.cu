@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host.h"
 
 namespace oxi {
 
@@ -76,7 +77,7 @@ bool build_geom(const oxi_ihdr *h, size_t data_len, int optimize_alpha, Geom *g)
         const size_t n = left / len;
         if (n > 0xFFFFFFFFu) return false;
         if (n) {
-            g->pass[0] = PassDesc{0, (uint32_t)n, (uint32_t)len, 0, 0};
+            g->pass[0] = PassDesc{0, (uint32_t)n, (uint32_t)len, h->width, 0};
             g->n_pass = 1;
             g->max_len = (uint32_t)len;
             row = (uint32_t)n;
@@ -93,7 +94,7 @@ bool build_geom(const oxi_ihdr *h, size_t data_len, int optimize_alpha, Geom *g)
             const bool exhausted = n < ph;
             if (n > ph) n = ph;
             if (n) {
-                g->pass[g->n_pass++] = PassDesc{row, (uint32_t)n, (uint32_t)len, 0, (uint64_t)off};
+                g->pass[g->n_pass++] = PassDesc{row, (uint32_t)n, (uint32_t)len, (uint32_t)pw, (uint64_t)off};
                 if (len > g->max_len) g->max_len = (uint32_t)len;
                 row += (uint32_t)n;
                 off += n * len;
@@ -109,27 +110,6 @@ bool build_geom(const oxi_ihdr *h, size_t data_len, int optimize_alpha, Geom *g)
 }
 
 // ---- per-device context -----------------------------------------------------------------------------------
-
-struct Slot {
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    uint8_t *scratch = nullptr;
-    size_t scratch_bytes = 0;
-    uint8_t *d_in = nullptr;
-    size_t in_cap = 0;
-    uint8_t *d_out = nullptr; // all strategies' outputs + filters_used, carved
-    size_t out_cap = 0;
-    uint8_t *d_pre = nullptr; // predefined filter ids
-    size_t pre_cap = 0;
-};
-
-struct DeviceCtx {
-    int device = -1;
-    int num_sms = 0;
-    std::mutex mu;
-    std::vector<Slot *> free_slots;
-    std::map<cudaStream_t, Slot *> stream_slots;
-};
 
 static std::mutex g_ctx_mu;
 static std::map<int, DeviceCtx *> g_ctx;
@@ -153,7 +133,7 @@ DeviceCtx *get_ctx(int device, int *err) {
     return c;
 }
 
-static cudaError_t grow(uint8_t **p, size_t *cap, size_t need) {
+cudaError_t grow(uint8_t **p, size_t *cap, size_t need) {
     if (need <= *cap) return cudaSuccess;
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -162,6 +142,14 @@ static cudaError_t grow(uint8_t **p, size_t *cap, size_t need) {
     cudaError_t e = cudaMalloc((void **)p, want);
     if (e == cudaSuccess) *cap = want;
     return e;
+}
+
+DeviceCtx *current_ctx(int *err) {
+    DeviceCtx *c = get_ctx(t_device, err);
+    if (!c) return nullptr;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) { *err = fail_cuda(e, "cudaSetDevice"); return nullptr; }
+    return c;
 }
 
 Slot *acquire_slot(DeviceCtx *c) {

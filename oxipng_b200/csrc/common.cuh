@@ -17,7 +17,7 @@ struct PassDesc {
     uint32_t row0;
     uint32_t nrows;
     uint32_t len;
-    uint32_t pad_;
+    uint32_t pixels; // pixels per scanline of this pass (ScanLine::num_pixels)
     uint64_t in_base;
 };
 

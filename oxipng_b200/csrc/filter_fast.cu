@@ -267,58 +267,97 @@ __device__ __forceinline__ void entropy_score(uint32_t *hist, uint32_t *s_ent) {
 }
 
 // One Bigrams/BigEnt trial for filter F over the stream t[0]=F, t[1+i]=residual[i]: windows (t[p-1], t[p]), p=1..len.
+// Work is split at word granularity so that every thread of the CTA has windows even for short rows: thread t owns row
+// words t, t+NT, ...; the residual words stay in registers for both passes.
 // Pass 1 counts into the u16 table (the adder that sees 0 owns the bigram); pass 2 lets owners read the final count,
-// contribute 1 to the distinct count and ilog2i(count) to the entropy, and clear the entry.
-template <int D, int NT, int F>
+// contribute 1 to the distinct count and ilog2i(count) to the entropy, and clear the entry for the next trial.
+template <int D, int NT, int F, int WPT>
 __device__ __forceinline__ void bigram_trial(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
                                              uint32_t *table, uint32_t *s_bgc, uint32_t *s_bge) {
-    const uint32_t nchunks = (len + 15) >> 4;
-    unsigned long long own = 0;
+    const uint32_t nwords = (len + 3) >> 2;
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur), *uw = reinterpret_cast<const uint32_t *>(up);
     uint16_t *t16 = reinterpret_cast<uint16_t *>(table);
-#pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-        int bit = 0;
-        uint32_t distinct = 0, ent = 0;
-        for (uint32_t c = threadIdx.x; c < nchunks; c += NT) {
-            const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
-            const int valid = (int)len - (int)(16 * c);
-            // byte of the stream just before this chunk: the filter id for chunk 0, else the previous residual
-            uint32_t prev = c == 0 ? (uint32_t)F : residual_at(F, cur, up, (int)(16 * c) - 1, bpp);
+    uint32_t r[WPT], pv[WPT];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t x = cw.w[k + 2];
-                const uint32_t r = __vsub4(x, pred4<F>(left_word<D>(cw, k, shift), uw.w[k + 2], left_word<D>(uw, k, shift)));
+    for (int i = 0; i < WPT; i++) {
+        const uint32_t k = threadIdx.x + i * NT;
+        uint32_t x = 0;
+        if (k < nwords) {
+            // row words k-1-D .. k are addressable: the slot has 32 zero bytes in front of the row
+            const int kk = (int)k;
+            uint32_t l = 0, u = 0, ul = 0;
+            x = cw[kk];
+            if (F == 1 || F == 3 || F == 4)
+                l = D == 2 ? cw[kk - 2] : D == 1 ? __funnelshift_l(cw[kk - 2], cw[kk - 1], shift)
+                                                 : __funnelshift_l(cw[kk - 1], cw[kk], shift);
+            if (F >= 2) u = uw[kk];
+            if (F == 4)
+                ul = D == 2 ? uw[kk - 2] : D == 1 ? __funnelshift_l(uw[kk - 2], uw[kk - 1], shift)
+                                                  : __funnelshift_l(uw[kk - 1], uw[kk], shift);
+            x = __vsub4(x, pred4<F>(l, u, ul));
+        }
+        r[i] = x;
+        // stream byte just before this word: the last residual byte of the previous word (neighbouring lane), the
+        // filter id in front of word 0
+        uint32_t p = __shfl_up_sync(0xffffffffu, x >> 24, 1);
+        if ((threadIdx.x & 31) == 0) p = k == 0 ? (uint32_t)F : (k < nwords ? residual_at(F, cur, up, 4 * (int)k - 1, bpp) : 0u);
+        pv[i] = p;
+    }
+    unsigned long long own = 0;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t b = (r >> (8 * j)) & 255u;
-                    const uint32_t bg = (prev << 8) | b;
-                    prev = b;
-                    if (4 * k + j < valid) {
-                        if (pass == 0) {
-                            const uint32_t old = atomicAdd(&table[bg >> 1], (bg & 1u) ? 0x10000u : 1u);
-                            const uint32_t cnt = (bg & 1u) ? (old >> 16) : (old & 0xFFFFu);
-                            if (cnt == 0) own |= 1ull << bit;
-                        } else if ((own >> bit) & 1ull) {
-                            const uint32_t cnt = t16[bg];
-                            t16[bg] = 0;
-                            distinct += 1;
-                            ent += ilog2i(cnt);
-                        }
-                    }
-                    bit++;
+    for (int i = 0; i < WPT; i++) {
+        const uint32_t k = threadIdx.x + i * NT;
+        const int valid = (int)len - 4 * (int)k;
+        uint32_t prev = pv[i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t b = (r[i] >> (8 * j)) & 255u;
+            const uint32_t bg = (prev << 8) | b;
+            prev = b;
+            if (j < valid) {
+                const uint32_t old = atomicAdd(&table[bg >> 1], (bg & 1u) ? 0x10000u : 1u);
+                const uint32_t cnt = (bg & 1u) ? (old >> 16) : (old & 0xFFFFu);
+                if (cnt == 0) own |= 1ull << (4 * i + j);
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t distinct = 0, ent = 0;
+    if (own) {
+#pragma unroll
+        for (int i = 0; i < WPT; i++) {
+            uint32_t prev = pv[i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t b = (r[i] >> (8 * j)) & 255u;
+                const uint32_t bg = (prev << 8) | b;
+                prev = b;
+                if ((own >> (4 * i + j)) & 1ull) {
+                    const uint32_t cnt = t16[bg];
+                    t16[bg] = 0;
+                    distinct += 1;
+                    ent += ilog2i(cnt);
                 }
             }
         }
-        if (pass == 1) {
-            distinct = warp_sum(distinct);
-            ent = warp_sum(ent);
-            if ((threadIdx.x & 31) == 0) {
-                atomicAdd(&s_bgc[F], distinct);
-                atomicAdd(&s_bge[F], ent);
-            }
-        }
-        __syncthreads();
     }
+    distinct = warp_sum(distinct);
+    ent = warp_sum(ent);
+    if ((threadIdx.x & 31) == 0 && distinct) {
+        atomicAdd(&s_bgc[F], distinct);
+        atomicAdd(&s_bge[F], ent);
+    }
+    __syncthreads();
+}
+
+template <int D, int NT, int WPT>
+__device__ __forceinline__ void bigram_row(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
+                                           uint32_t *table, uint32_t *s_bgc, uint32_t *s_bge) {
+    bigram_trial<D, NT, 0, WPT>(cur, up, len, shift, bpp, table, s_bgc, s_bge);
+    bigram_trial<D, NT, 1, WPT>(cur, up, len, shift, bpp, table, s_bgc, s_bge);
+    bigram_trial<D, NT, 2, WPT>(cur, up, len, shift, bpp, table, s_bgc, s_bge);
+    bigram_trial<D, NT, 3, WPT>(cur, up, len, shift, bpp, table, s_bgc, s_bge);
+    bigram_trial<D, NT, 4, WPT>(cur, up, len, shift, bpp, table, s_bgc, s_bge);
 }
 
 // ---- writing the chosen row --------------------------------------------------------------------------------------
@@ -493,11 +532,11 @@ __global__ void __launch_bounds__(threads_for(SC), 1) k_fast(const __grid_consta
                         entropy_score<NT>(sm.hist, sm.s_ent);
                     }
                     if (SC & SC_BIGRAM) {
-                        bigram_trial<D, NT, 0>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
-                        bigram_trial<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
-                        bigram_trial<D, NT, 2>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
-                        bigram_trial<D, NT, 3>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
-                        bigram_trial<D, NT, 4>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
+                        const uint32_t wpt = (((len + 3) >> 2) + NT - 1) / NT; // row words per thread
+                        if (wpt <= 1) bigram_row<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
+                        else if (wpt <= 2) bigram_row<D, NT, 2>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
+                        else if (wpt <= 4) bigram_row<D, NT, 4>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
+                        else bigram_row<D, NT, 8>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
                     }
                     __syncthreads();
                 }
@@ -588,7 +627,7 @@ bool fast_supported(const Geom &g, const StrategySet &set) {
     if (g.bpp != 1 && g.bpp != 2 && g.bpp != 3 && g.bpp != 4 && g.bpp != 6 && g.bpp != 8) return false;
     const int sc = kernel_sc(scorers_needed(set));
     if (smem_bytes_for(sc, slot_bytes(g)) > SMEM_LIMIT) return false;
-    if ((sc & SC_BIGRAM) && g.max_len > 65535u) return false; // u16 counters and the 64-bit owner mask
+    if ((sc & SC_BIGRAM) && g.max_len > 32768u) return false; // <= 8 row words per thread; u16 counters
     return true;
 }
 
@@ -621,10 +660,20 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
             occ = it->second;
         }
     }
-    // Bands: enough work items to fill every resident CTA slot a few times over, but not so many that the one-row
-    // halo per band becomes a large share of the reads.  Bands never cross a pass (png/mod.rs:375-378).
+    // Bands never cross a pass (png/mod.rs:375-378) and cost one halo row each.  Memory-bound scorers take ~32-row
+    // bands (3% extra reads); the shared-memory-bound ones (Entropy, bigrams) take ~8-row bands so that the static
+    // grid-stride split stays balanced.  When the whole job is only a few waves, the band count is rounded to a
+    // multiple of the resident CTA slots instead (every CTA gets the same number of near-equal bands).
     const uint64_t slots = (uint64_t)ctx.num_sms * occ;
-    const uint64_t want_items = slots * 4;
+    const uint64_t rows_total = (uint64_t)n_images * g.total_rows;
+    const uint32_t R = (sc & (SC_BIGRAM | SC_ENTROPY)) ? 8 : 32;
+    uint64_t want_items = (rows_total + R - 1) / R;
+    if (want_items < 6 * slots) {
+        uint64_t waves = want_items / slots;
+        if (waves < 1) waves = 1;
+        want_items = waves * slots;
+        if (want_items * 2 > rows_total) want_items = rows_total / 2 ? rows_total / 2 : 1; // keep >= 2 rows per band
+    }
     uint64_t per_image = (want_items + n_images - 1) / n_images;
     if (per_image < 1) per_image = 1;
     uint32_t acc = 0;
@@ -633,7 +682,7 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
         if (p < g.n_pass) {
             const uint64_t bytes = (uint64_t)g.pass[p].nrows * g.pass[p].len;
             uint64_t nb = (per_image * bytes + g.data_len - 1) / (g.data_len ? g.data_len : 1);
-            const uint64_t max_nb = (g.pass[p].nrows + 3) / 4; // keep >= 4 rows per band when possible
+            const uint64_t max_nb = (g.pass[p].nrows + 1) / 2;
             if (nb > max_nb) nb = max_nb;
             if (nb < 1) nb = 1;
             acc += (uint32_t)nb;
