@@ -7,5 +7,7 @@ from ._lib import OxiError, FLAG_FORCE_FAST, FLAG_FORCE_GENERIC, lib  # noqa: F4
 from .png import (BitDepth, ColorType, FilterStrategy, IhdrData, PngImage, RowFilter, filter_batch,  # noqa: F401
                   filter_batch_device, filter_image_multi, filter_tier)
 
-__all__ = ["BitDepth", "ColorType", "FilterStrategy", "IhdrData", "PngImage", "RowFilter", "filter_batch",
+from . import reduction  # noqa: F401,E402
+
+__all__ = ["reduction", "BitDepth", "ColorType", "FilterStrategy", "IhdrData", "PngImage", "RowFilter", "filter_batch",
            "filter_batch_device", "filter_image_multi", "filter_tier", "OxiError", "lib"]

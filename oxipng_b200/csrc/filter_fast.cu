@@ -41,6 +41,7 @@ struct FastParams {
     uint32_t items_per_image;
     uint32_t rb;    // bytes of one ring slot
     uint32_t shift; // 8 * (bpp % 4): funnel-shift amount that turns a row word into its "left" word
+    uint32_t small_tab; // bigram scorer: five dense 64x64 in-range tables are carved (rows <= 8192 bytes)
 };
 
 __host__ __device__ constexpr int threads_for(int sc) { return (sc & SC_BIGRAM) ? 1024 : 256; }
@@ -161,24 +162,28 @@ struct Smem {
     uint8_t *rows;     // 3 slots of rb bytes
     uint32_t *hist;    // [5][HIST_REP][256]
     uint32_t *table;   // 32768 words = 65536 u16 counters
+    uint32_t *small;   // [5][2048] words = five 64x64 u16 counter tables (in-range bigrams), optional
+    uint32_t *s_out;   // [5] outlier-window count per trial
 };
 template <int SC>
 __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb) {
     Smem s;
     s.bar = reinterpret_cast<uint64_t *>(base);
     uint32_t *u = reinterpret_cast<uint32_t *>(base + 64);
-    s.s_min = u; s.s_ent = u + 8; s.s_bgc = u + 16; s.s_bge = u + 24;
+    s.s_min = u; s.s_ent = u + 8; s.s_bgc = u + 16; s.s_bge = u + 24; s.s_out = u + 32;
     s.rows = base + SMEM_HDR;
     uint8_t *p = s.rows + 3 * (size_t)rb;
     s.hist = reinterpret_cast<uint32_t *>(p);
     if (SC & SC_ENTROPY) p += 5 * HIST_REP * 256 * 4;
     s.table = reinterpret_cast<uint32_t *>(p);
+    s.small = reinterpret_cast<uint32_t *>(p + 65536 * 2);
     return s;
 }
-__host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb) {
+constexpr uint32_t SMALL_BYTES = 5 * 4096 * 2;
+__host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, bool small_tab) {
     uint32_t b = SMEM_HDR + 3 * rb;
     if (sc & SC_ENTROPY) b += 5 * HIST_REP * 256 * 4;
-    if (sc & SC_BIGRAM) b += 65536 * 2;
+    if (sc & SC_BIGRAM) b += 65536 * 2 + (small_tab ? SMALL_BYTES : 0);
     return b;
 }
 
@@ -360,6 +365,150 @@ __device__ __forceinline__ void bigram_row(const uint8_t *cur, const uint8_t *up
     bigram_trial<D, NT, 4, WPT>(cur, up, len, shift, bpp, table, s_bgc, s_bge);
 }
 
+// ---- Bigrams/BigEnt, all five trials at once (rows <= 8192 bytes) ---------------------------------------------------
+// Filtered rows of natural images are sharply peaked around 0, which makes returning atomics on one shared table
+// serialise (ncu: ~11 wavefronts per ATOMS).  Here a window whose two stream bytes both lie in [-32, 31] (as i8) is
+// counted in a dense 64x64 u16 table private to its trial with a *non-returning* add (same-address lanes combine), and
+// all five trials run in one phase; a sweep over the 5 x 4096 counters then yields distinct count and entropy with
+// no ownership bookkeeping.  The remaining (outlier) windows take the big-table / owner path, trial by trial, and
+// only for trials that have any.  Exact for any data: every window is counted in exactly one of the two tables, and
+// the two key sets are disjoint.
+__device__ __forceinline__ uint32_t range_code4(uint32_t r) { // per byte: (b + 32) mod 256 (no carries across bytes)
+    return ((r & 0x7F7F7F7Fu) + 0x20202020u) ^ (r & 0x80808080u);
+}
+template <int D, int NT, int WPT>
+__device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
+                                                 const Smem &sm) {
+    const uint32_t nwords = (len + 3) >> 2;
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur), *uw = reinterpret_cast<const uint32_t *>(up);
+    uint32_t r[WPT][5], pv[WPT][5];
+    uint32_t om[5] = {0, 0, 0, 0, 0}; // outlier windows of this thread, bit 4*i+j
+#pragma unroll
+    for (int i = 0; i < WPT; i++) {
+        const uint32_t k = threadIdx.x + i * NT;
+        const int kk = (int)k;
+        uint32_t x = 0, l = 0, u = 0, ul = 0;
+        if (k < nwords) {
+            x = cw[kk];
+            u = uw[kk];
+            l = D == 2 ? cw[kk - 2] : D == 1 ? __funnelshift_l(cw[kk - 2], cw[kk - 1], shift)
+                                             : __funnelshift_l(cw[kk - 1], cw[kk], shift);
+            ul = D == 2 ? uw[kk - 2] : D == 1 ? __funnelshift_l(uw[kk - 2], uw[kk - 1], shift)
+                                              : __funnelshift_l(uw[kk - 1], uw[kk], shift);
+        }
+        r[i][0] = x;
+        r[i][1] = __vsub4(x, l);
+        r[i][2] = __vsub4(x, u);
+        r[i][3] = __vsub4(x, __vhaddu4(l, u));
+        r[i][4] = __vsub4(x, paeth4(l, u, ul));
+#pragma unroll
+        for (int f = 0; f < 5; f++) {
+            uint32_t p = __shfl_up_sync(0xffffffffu, r[i][f] >> 24, 1);
+            if ((threadIdx.x & 31) == 0)
+                p = k == 0 ? (uint32_t)f : (k < nwords ? residual_at(f, cur, up, 4 * kk - 1, bpp) : 0u);
+            pv[i][f] = p;
+        }
+        const int valid = (int)len - 4 * kk;
+#pragma unroll
+        for (int f = 0; f < 5; f++) {
+            const uint32_t t = range_code4(r[i][f]);
+            uint32_t tp = (pv[i][f] + 32u) & 255u; // code/flags of the byte before the word
+            uint32_t *tab = sm.small + f * 2048;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t tj = (t >> (8 * j)) & 255u;
+                if (j < valid) {
+                    if (((tp | tj) & 0xC0u) == 0) {
+                        const uint32_t idx = (tp << 6) | tj;
+                        atomicAdd(&tab[idx >> 1], (idx & 1u) ? 0x10000u : 1u);
+                    } else {
+                        om[f] |= 1u << (4 * i + j);
+                    }
+                }
+                tp = tj;
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < 5; f++) {
+        const uint32_t n = warp_sum((uint32_t)__popc(om[f]));
+        if ((threadIdx.x & 31) == 0 && n) atomicAdd(&sm.s_out[f], n);
+    }
+    __syncthreads();
+    // sweep the five dense tables
+    {
+        uint32_t dis[5] = {0, 0, 0, 0, 0}, ent[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int f = 0; f < 5; f++) {
+            for (uint32_t w = threadIdx.x; w < 2048; w += NT) {
+                const uint32_t v = sm.small[f * 2048 + w];
+                if (v) {
+                    sm.small[f * 2048 + w] = 0;
+                    const uint32_t c0 = v & 0xFFFFu, c1 = v >> 16;
+                    if (c0) { dis[f]++; ent[f] += ilog2i(c0); }
+                    if (c1) { dis[f]++; ent[f] += ilog2i(c1); }
+                }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < 5; f++) {
+            const uint32_t d = warp_sum(dis[f]), e = warp_sum(ent[f]);
+            if ((threadIdx.x & 31) == 0 && d) {
+                atomicAdd(&sm.s_bgc[f], d);
+                atomicAdd(&sm.s_bge[f], e);
+            }
+        }
+    }
+    // outlier windows: big table, owner pass, one trial at a time
+    uint16_t *t16 = reinterpret_cast<uint16_t *>(sm.table);
+#pragma unroll
+    for (int f = 0; f < 5; f++) {
+        if (sm.s_out[f] == 0) continue; // uniform: written before the barrier above
+        uint32_t own = 0;
+#pragma unroll
+        for (int i = 0; i < WPT; i++) {
+            uint32_t prev = pv[i][f];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t b = (r[i][f] >> (8 * j)) & 255u;
+                const uint32_t bg = (prev << 8) | b;
+                prev = b;
+                if ((om[f] >> (4 * i + j)) & 1u) {
+                    const uint32_t old = atomicAdd(&sm.table[bg >> 1], (bg & 1u) ? 0x10000u : 1u);
+                    if (((bg & 1u) ? (old >> 16) : (old & 0xFFFFu)) == 0) own |= 1u << (4 * i + j);
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t distinct = 0, ent = 0;
+        if (own) {
+#pragma unroll
+            for (int i = 0; i < WPT; i++) {
+                uint32_t prev = pv[i][f];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t b = (r[i][f] >> (8 * j)) & 255u;
+                    const uint32_t bg = (prev << 8) | b;
+                    prev = b;
+                    if ((own >> (4 * i + j)) & 1u) {
+                        const uint32_t cnt = t16[bg];
+                        t16[bg] = 0;
+                        distinct += 1;
+                        ent += ilog2i(cnt);
+                    }
+                }
+            }
+        }
+        distinct = warp_sum(distinct);
+        ent = warp_sum(ent);
+        if ((threadIdx.x & 31) == 0 && distinct) {
+            atomicAdd(&sm.s_bgc[f], distinct);
+            atomicAdd(&sm.s_bge[f], ent);
+        }
+        __syncthreads();
+    }
+}
+
 // ---- writing the chosen row --------------------------------------------------------------------------------------
 // out_row points at the filter-type byte of this row in the filtered stream.  Interior 16-byte granules of the
 // output are produced in the output's alignment frame; the (at most 31) edge bytes are written one by one.
@@ -431,13 +580,16 @@ __global__ void __launch_bounds__(threads_for(SC), 1) k_fast(const __grid_consta
         mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_init(&sm.bar[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 32) sm.s_min[tid] = 0;
+    if (tid < 40) sm.s_min[tid] = 0;
     for (uint32_t i = tid; i < 3 * PAD / 4; i += NT) // zero the left pad of each slot (never written again)
         reinterpret_cast<uint32_t *>(sm.rows + (i / (PAD / 4)) * (size_t)P.rb)[i % (PAD / 4)] = 0;
     if (SC & SC_ENTROPY)
         for (uint32_t i = tid; i < 5 * HIST_REP * 256; i += NT) sm.hist[i] = 0;
-    if (SC & SC_BIGRAM)
+    if (SC & SC_BIGRAM) {
         for (uint32_t i = tid; i < 32768; i += NT) sm.table[i] = 0;
+        if (P.small_tab)
+            for (uint32_t i = tid; i < SMALL_BYTES / 4; i += NT) sm.small[i] = 0;
+    }
     __syncthreads();
 
     uint32_t parity = 0; // bit s = phase to wait for on slot s
@@ -522,7 +674,7 @@ __global__ void __launch_bounds__(threads_for(SC), 1) k_fast(const __grid_consta
                     }
                     nz |= v.x | v.y | v.z | v.w;
                 }
-                if (tid < 32) sm.s_min[tid] = 0; // clears s_min, s_ent, s_bgc, s_bge
+                if (tid < 40) sm.s_min[tid] = 0; // clears s_min, s_ent, s_bgc, s_bge, s_out
                 heur = __syncthreads_or(nz != 0) != 0;
                 if (heur) {
                     if (SC & SC_MINSUM) minsum_pass<D, NT>(cur, up, len, shift, sm.s_min);
@@ -533,7 +685,9 @@ __global__ void __launch_bounds__(threads_for(SC), 1) k_fast(const __grid_consta
                     }
                     if (SC & SC_BIGRAM) {
                         const uint32_t wpt = (((len + 3) >> 2) + NT - 1) / NT; // row words per thread
-                        if (wpt <= 1) bigram_row<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
+                        if (P.small_tab && wpt <= 1) bigram_row_small<D, NT, 1>(cur, up, len, shift, bpp, sm);
+                        else if (P.small_tab && wpt <= 2) bigram_row_small<D, NT, 2>(cur, up, len, shift, bpp, sm);
+                        else if (wpt <= 1) bigram_row<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
                         else if (wpt <= 2) bigram_row<D, NT, 2>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
                         else if (wpt <= 4) bigram_row<D, NT, 4>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
                         else bigram_row<D, NT, 8>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
@@ -626,7 +780,7 @@ bool fast_supported(const Geom &g, const StrategySet &set) {
     if (g.alpha_bytes != 0 || g.total_rows == 0) return false;
     if (g.bpp != 1 && g.bpp != 2 && g.bpp != 3 && g.bpp != 4 && g.bpp != 6 && g.bpp != 8) return false;
     const int sc = kernel_sc(scorers_needed(set));
-    if (smem_bytes_for(sc, slot_bytes(g)) > SMEM_LIMIT) return false;
+    if (smem_bytes_for(sc, slot_bytes(g), false) > SMEM_LIMIT) return false;
     if ((sc & SC_BIGRAM) && g.max_len > 32768u) return false; // <= 8 row words per thread; u16 counters
     return true;
 }
@@ -642,7 +796,8 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
     P.n_images = n_images;
     P.rb = slot_bytes(g);
     P.shift = 8 * (g.bpp % 4);
-    const uint32_t smem = smem_bytes_for(sc, P.rb);
+    P.small_tab = (sc & SC_BIGRAM) && g.max_len <= 8192 && smem_bytes_for(sc, P.rb, true) <= SMEM_LIMIT;
+    const uint32_t smem = smem_bytes_for(sc, P.rb, P.small_tab != 0);
     KernelFn fn = pick_kernel((int)(g.bpp / 4), sc);
     cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -1,0 +1,1006 @@
+// reduce.cu -- the pixel-scan reductions of src/reduction/{alpha,bit_depth,color,palette}.rs as grid-wide CUDA scans,
+// with the <=256-entry palette bookkeeping (dedupe sets, luma sort, tRNS choice) kept on the host exactly where the
+// reference keeps it.  Every entry point takes host buffers (include/oxipng_b200.h), uploads the image once, runs the
+// scan/transform kernels and downloads the result.  Return OXI_NONE where the reference returns `None`.
+//
+// Kernels are HBM-bound byte maps / reductions: 128-bit accesses where the pixel size divides 16, early-out flags in
+// global memory, per-CTA shared-memory partials (flags, 256-bin histograms, distinct-colour hash sets) merged with a
+// handful of global atomics per CTA.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace oxi {
+namespace {
+
+constexpr int RT = 256; // threads per CTA for the scans
+
+inline unsigned grid_for(uint64_t work_items, int num_sms, int per_sm = 8) {
+    uint64_t g = (work_items + RT - 1) / RT;
+    const uint64_t cap = (uint64_t)num_sms * per_sm;
+    if (g > cap) g = cap;
+    return g ? (unsigned)g : 1u;
+}
+
+// Device-side scratch shared by the scans of one call
+struct ScanState {
+    uint32_t fail;             // "not reducible" / invalid
+    uint32_t has_transparency; // alpha.rs:50-52
+    uint32_t used[8];          // 256-bit set (alpha.rs:57-59 used_colors)
+    uint32_t max_bits;         // bit_depth.rs:82-112
+    uint32_t n_distinct;       // color.rs:18-35
+    uint32_t overflow;         // 257th distinct colour
+    uint32_t pad_[3];
+    unsigned long long hist[256];
+    uint32_t counts[256];
+};
+
+__device__ __forceinline__ bool alpha_zero(const uint8_t *px, uint32_t cb, uint32_t bpp) {
+    for (uint32_t k = cb; k < bpp; k++)
+        if (px[k]) return false;
+    return true;
+}
+
+// ---- alpha.rs -----------------------------------------------------------------------------------------------
+
+// cleaned_alpha_channel (alpha.rs:11-32): pixels whose alpha bytes are all zero become all zero.
+// One thread per 16 bytes (whole pixels: bpp in {2,4,8}); `amask` marks the alpha bytes inside one pixel-sized lane.
+__global__ void __launch_bounds__(RT) k_clean_alpha(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint64_t n16,
+                                                     const uint8_t *__restrict__ in_tail, uint8_t *__restrict__ out_tail,
+                                                     uint32_t tail_bytes, uint32_t bpp, uint32_t cb) {
+    const uint64_t stride = (uint64_t)gridDim.x * RT;
+    for (uint64_t i = (uint64_t)blockIdx.x * RT + threadIdx.x; i < n16; i += stride) {
+        uint4 v = in[i];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        if (bpp == 2) { // GA8: alpha = byte 1 of every u16
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t x = w[k];
+                if ((x & 0x0000FF00u) == 0) x &= 0xFFFF0000u;
+                if ((x & 0xFF000000u) == 0) x &= 0x0000FFFFu;
+                w[k] = x;
+            }
+        } else if (bpp == 4) { // GA16: bytes 2,3; RGBA8: byte 3
+            const uint32_t am = cb == 2 ? 0xFFFF0000u : 0xFF000000u;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if ((w[k] & am) == 0) w[k] = 0;
+        } else { // RGBA16: bytes 6,7 of every 8
+            if ((w[1] & 0xFFFF0000u) == 0) w[0] = w[1] = 0;
+            if ((w[3] & 0xFFFF0000u) == 0) w[2] = w[3] = 0;
+        }
+        out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { // < 16 trailing bytes
+        for (uint32_t p = 0; p + bpp <= tail_bytes; p += bpp) {
+            const bool z = alpha_zero(in_tail + p, cb, bpp);
+            for (uint32_t k = 0; k < bpp; k++) out_tail[p + k] = z ? 0 : in_tail[p + k];
+        }
+    }
+}
+
+// reduced_alpha_channel scan (alpha.rs:49-60)
+__global__ void __launch_bounds__(RT) k_alpha_scan(const uint8_t *__restrict__ in, uint64_t npix, uint32_t bpp, uint32_t cb,
+                                                    int optimize_alpha, ScanState *st) {
+    __shared__ uint32_t s_used[8];
+    __shared__ uint32_t s_flags[2];
+    if (threadIdx.x < 8) s_used[threadIdx.x] = 0;
+    if (threadIdx.x < 2) s_flags[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t fail = 0, transp = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * RT;
+    for (uint64_t i = (uint64_t)blockIdx.x * RT + threadIdx.x; i < npix; i += stride) {
+        const uint8_t *px = in + i * bpp;
+        if (optimize_alpha && alpha_zero(px, cb, bpp)) {
+            transp = 1;
+            continue;
+        }
+        bool partial = false;
+        for (uint32_t k = cb; k < bpp; k++) partial |= px[k] != 255;
+        if (partial) {
+            fail = 1;
+        } else if (optimize_alpha) {
+            bool gray = true;
+            for (uint32_t k = 1; k < cb; k++) gray &= px[k] == px[0];
+            if (gray) atomicOr(&s_used[px[0] >> 5], 1u << (px[0] & 31));
+        }
+    }
+    if (fail) s_flags[0] = 1;
+    if (transp) s_flags[1] = 1;
+    __syncthreads();
+    if (threadIdx.x < 8 && s_used[threadIdx.x]) atomicOr(&st->used[threadIdx.x], s_used[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        if (s_flags[0]) st->fail = 1;
+        if (s_flags[1]) st->has_transparency = 1;
+    }
+}
+
+// reduced_alpha_channel transform (alpha.rs:77-85): drop the alpha bytes; transparent pixels become `trns` repeated
+__global__ void __launch_bounds__(RT) k_alpha_strip(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+                                                     uint64_t npix, uint32_t bpp, uint32_t cb, int trns) {
+    const uint64_t stride = (uint64_t)gridDim.x * RT;
+    for (uint64_t i = (uint64_t)blockIdx.x * RT + threadIdx.x; i < npix; i += stride) {
+        const uint8_t *px = in + i * bpp;
+        uint8_t *o = out + i * cb;
+        const bool t = trns >= 0 && alpha_zero(px, cb, bpp);
+        for (uint32_t k = 0; k < cb; k++) o[k] = t ? (uint8_t)trns : px[k];
+    }
+}
+
+// ---- bit_depth.rs ---------------------------------------------------------------------------------------------
+
+// reduced_bit_depth_16_to_8 / scaled_bit_depth_16_to_8 (bit_depth.rs:9-64): 8 samples (16 B in, 8 B out) per thread.
+// The f32 expression round(v * (255/65535)) equals (510 v + 65535) / 131070 for all 65536 inputs (tests pin this).
+__device__ __forceinline__ uint32_t scale16(uint32_t hi, uint32_t lo) {
+    if (hi == lo) return hi;
+    const uint32_t v = (hi << 8) | lo;
+    return (510u * v + 65535u) / 131070u;
+}
+__global__ void __launch_bounds__(RT) k_16to8(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint64_t nsamples,
+                                               int scale, ScanState *st) {
+    const uint64_t n8 = nsamples / 8, stride = (uint64_t)gridDim.x * RT;
+    uint32_t bad = 0;
+    const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
+    uint2 *out2 = reinterpret_cast<uint2 *>(out);
+    for (uint64_t i = (uint64_t)blockIdx.x * RT + threadIdx.x; i < n8; i += stride) {
+        const uint4 v = in4[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t h0 = w[k] & 255u, l0 = (w[k] >> 8) & 255u, h1 = (w[k] >> 16) & 255u, l1 = w[k] >> 24;
+            bad |= (h0 ^ l0) | (h1 ^ l1);
+            const uint32_t a = scale ? scale16(h0, l0) : h0, b = scale ? scale16(h1, l1) : h1;
+            o[k >> 1] |= (a | (b << 8)) << (16 * (k & 1));
+        }
+        out2[i] = make_uint2(o[0], o[1]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (uint64_t s = n8 * 8; s < nsamples; s++) {
+            const uint32_t h = in[2 * s], l = in[2 * s + 1];
+            bad |= h ^ l;
+            out[s] = (uint8_t)(scale ? scale16(h, l) : h);
+        }
+    if (!scale && __syncthreads_or(bad != 0) && threadIdx.x == 0) st->fail = 1;
+}
+
+// per-byte minimal bit period of a gray sample (bit_depth.rs:82-112 is the running maximum of this over all bytes)
+__device__ __forceinline__ uint32_t min_bits_of(uint32_t b) {
+    if (b == 0 || b == 255) return 1;
+    if (b == (b & 3u) * 0x55u) return 2;
+    if (b == (b & 15u) * 0x11u) return 4;
+    return 8;
+}
+__global__ void __launch_bounds__(RT) k_min_bits(const uint8_t *__restrict__ in, uint64_t n, ScanState *st) {
+    uint32_t m = 1;
+    const uint64_t n16 = n / 16, stride = (uint64_t)gridDim.x * RT;
+    const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
+    for (uint64_t i = (uint64_t)blockIdx.x * RT + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = in4[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) m = max(m, min_bits_of((w[k] >> (8 * j)) & 255u));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (uint64_t i = n16 * 16; i < n; i++) m = max(m, min_bits_of(in[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 1) atomicMax(&st->max_bits, m);
+}
+
+struct RowMap { // per pass: rows of `in_len` bytes -> rows of `out_len` bytes
+    uint32_t n_pass;
+    uint32_t in_len[7], out_len[7], nrows[7], pixels[7];
+    uint64_t in_base[7], out_base[7], out_items[8]; // out_items: prefix sum of nrows*out_len
+};
+
+__device__ __forceinline__ int pass_of_item(const RowMap &m, uint64_t item) {
+    int p = 0;
+#pragma unroll
+    for (int i = 1; i < 7; i++)
+        if (i < (int)m.n_pass && item >= m.out_items[i]) p = i;
+    return p;
+}
+
+// reduced_bit_depth_8_or_less packing (bit_depth.rs:117-131): one thread per output byte
+__global__ void __launch_bounds__(RT) k_pack_bits(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, RowMap m,
+                                                   uint32_t bits) {
+    const uint32_t per = 8 / bits, mask = (1u << bits) - 1u;
+    const uint64_t total = m.out_items[m.n_pass], stride = (uint64_t)gridDim.x * RT;
+    for (uint64_t it = (uint64_t)blockIdx.x * RT + threadIdx.x; it < total; it += stride) {
+        const int p = pass_of_item(m, it);
+        const uint64_t local = it - m.out_items[p];
+        const uint64_t row = local / m.out_len[p];
+        const uint32_t ob = (uint32_t)(local % m.out_len[p]);
+        const uint8_t *src = in + m.in_base[p] + row * m.in_len[p];
+        uint32_t nb = 0, shift = 8;
+        for (uint32_t k = ob * per; k < ob * per + per && k < m.in_len[p]; k++) {
+            shift -= bits;
+            nb |= (src[k] & mask) << shift;
+        }
+        out[m.out_base[p] + local] = (uint8_t)nb;
+    }
+}
+
+// expanded_bit_depth_to_8 (bit_depth.rs:170-230): one thread per output pixel
+__global__ void __launch_bounds__(RT) k_expand_bits(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, RowMap m,
+                                                     uint32_t depth, int is_gray) {
+    const uint32_t mask = (1u << depth) - 1u;
+    const uint32_t rep = depth == 1 ? 0xFFu : depth == 2 ? 0x55u : 0x11u;
+    const uint64_t total = m.out_items[m.n_pass], stride = (uint64_t)gridDim.x * RT;
+    for (uint64_t it = (uint64_t)blockIdx.x * RT + threadIdx.x; it < total; it += stride) {
+        const int p = pass_of_item(m, it);
+        const uint64_t local = it - m.out_items[p];
+        const uint64_t row = local / m.out_len[p];
+        const uint32_t x = (uint32_t)(local % m.out_len[p]);
+        const uint32_t bit = x * depth;
+        const uint32_t byte = in[m.in_base[p] + row * m.in_len[p] + (bit >> 3)];
+        uint32_t val = (byte >> (8 - depth - (bit & 7u))) & mask;
+        if (is_gray) val *= rep;
+        out[m.out_base[p] + local] = (uint8_t)val;
+    }
+}
+
+// ---- color.rs ---------------------------------------------------------------------------------------------------
+
+// reduced_rgb_to_grayscale (color.rs:100-137): check R==G==B per pixel, keep the last colour sample (+ alpha)
+__global__ void __launch_bounds__(RT) k_rgb_to_gray(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint64_t npix,
+                                                     uint32_t bpp, uint32_t bd, ScanState *st) {
+    const uint64_t stride = (uint64_t)gridDim.x * RT;
+    const uint32_t last = 2 * bd, keep = bpp - last;
+    uint32_t bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * RT + threadIdx.x; i < npix; i += stride) {
+        const uint8_t *px = in + i * bpp;
+        if (bd == 1) bad |= (px[0] ^ px[1]) | (px[1] ^ px[2]);
+        else bad |= (px[0] ^ px[2]) | (px[1] ^ px[3]) | (px[2] ^ px[4]) | (px[3] ^ px[5]);
+        for (uint32_t k = 0; k < keep; k++) out[i * keep + k] = px[last + k];
+    }
+    if (__syncthreads_or(bad != 0) && threadIdx.x == 0) st->fail = 1;
+}
+
+// Distinct-colour set with first-occurrence index (build_palette, color.rs:18-35).
+// Global table: 4096 slots of (occupied|key) u64 + first pixel index u64.  Each CTA dedupes its contiguous pixel range
+// in a 1024-slot shared-memory table (smem atomics only), then merges its <=256 entries.
+constexpr uint32_t GSLOTS = 4096, LSLOTS = 1024;
+struct ColorTable {
+    unsigned long long key[GSLOTS];   // 0 = empty, else (1<<32) | key
+    unsigned long long first[GSLOTS]; // smallest pixel index holding this colour
+    uint32_t index[GSLOTS];           // palette index (filled by the host after sorting by `first`)
+};
+__device__ __forceinline__ uint32_t hash_color(uint32_t key) { return (key * 2654435761u) ^ (key >> 15); }
+__device__ __forceinline__ uint32_t load_key(const uint8_t *px, uint32_t ch) {
+    uint32_t k = px[0];
+    if (ch > 1) k |= (uint32_t)px[1] << 8;
+    if (ch > 2) k |= (uint32_t)px[2] << 16;
+    if (ch > 3) k |= (uint32_t)px[3] << 24;
+    return k;
+}
+
+__global__ void __launch_bounds__(RT) k_collect_colors(const uint8_t *__restrict__ in, uint64_t npix, uint32_t ch,
+                                                        ColorTable *tab, ScanState *st) {
+    __shared__ unsigned long long l_key[LSLOTS];
+    __shared__ unsigned long long l_first[LSLOTS];
+    __shared__ uint32_t l_count;
+    for (uint32_t i = threadIdx.x; i < LSLOTS; i += RT) { l_key[i] = 0; l_first[i] = ~0ull; }
+    if (threadIdx.x == 0) l_count = 0;
+    __syncthreads();
+    const uint64_t per = (npix + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = (uint64_t)blockIdx.x * per, hi = min(lo + per, npix);
+    uint32_t last_key = 0;
+    bool have_last = false;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += RT) {
+        if (l_count > 256 || *(volatile uint32_t *)&st->overflow) break; // 257th distinct colour: give up (color.rs:29-31)
+        const uint32_t key = load_key(in + i * ch, ch);
+        if (have_last && key == last_key) continue; // this thread already recorded an earlier occurrence
+        last_key = key;
+        have_last = true;
+        const unsigned long long tagged = (1ull << 32) | key;
+        uint32_t s = hash_color(key) & (LSLOTS - 1);
+        for (;;) {
+            unsigned long long cur = l_key[s];
+            if (cur == 0) {
+                cur = atomicCAS(&l_key[s], 0ull, tagged);
+                if (cur == 0) { atomicAdd(&l_count, 1u); cur = tagged; }
+            }
+            if (cur == tagged) { atomicMin(&l_first[s], (unsigned long long)i); break; }
+            s = (s + 1) & (LSLOTS - 1);
+            if (l_count > 256) break;
+        }
+    }
+    __syncthreads();
+    if (l_count > 256) {
+        if (threadIdx.x == 0) st->overflow = 1;
+        return;
+    }
+    for (uint32_t i = threadIdx.x; i < LSLOTS; i += RT) {
+        const unsigned long long tagged = l_key[i];
+        if (!tagged) continue;
+        uint32_t s = hash_color((uint32_t)tagged) & (GSLOTS - 1);
+        for (uint32_t probes = 0; probes < GSLOTS; probes++) {
+            unsigned long long cur = tab->key[s];
+            if (cur == 0) {
+                cur = atomicCAS(&tab->key[s], 0ull, tagged);
+                if (cur == 0) {
+                    if (atomicAdd(&st->n_distinct, 1u) >= 256) st->overflow = 1;
+                    cur = tagged;
+                }
+            }
+            if (cur == tagged) { atomicMin(&tab->first[s], l_first[i]); break; }
+            s = (s + 1) & (GSLOTS - 1);
+            if (*(volatile uint32_t *)&st->overflow) break;
+        }
+    }
+}
+
+// pixel -> palette index through the (now read-only) colour table, staged in shared memory
+__global__ void __launch_bounds__(RT) k_index_colors(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint64_t npix,
+                                                      uint32_t ch, const ColorTable *__restrict__ tab) {
+    extern __shared__ unsigned long long s_tab[]; // GSLOTS keys, then GSLOTS u8 indices
+    uint8_t *s_idx = reinterpret_cast<uint8_t *>(s_tab + GSLOTS);
+    for (uint32_t i = threadIdx.x; i < GSLOTS; i += RT) {
+        s_tab[i] = tab->key[i];
+        s_idx[i] = (uint8_t)tab->index[i];
+    }
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * RT;
+    for (uint64_t i = (uint64_t)blockIdx.x * RT + threadIdx.x; i < npix; i += stride) {
+        const uint32_t key = load_key(in + i * ch, ch);
+        const unsigned long long tagged = (1ull << 32) | key;
+        uint32_t s = hash_color(key) & (GSLOTS - 1);
+        while (s_tab[s] != tagged) s = (s + 1) & (GSLOTS - 1);
+        out[i] = s_idx[s];
+    }
+}
+
+// ---- palette.rs ---------------------------------------------------------------------------------------------------
+
+// 256-bin histogram of the index bytes (palette.rs:20-23 needs presence; counts are exposed too)
+__global__ void __launch_bounds__(RT) k_hist256(const uint8_t *__restrict__ in, uint64_t n, ScanState *st) {
+    __shared__ uint32_t h[4][256];
+    for (uint32_t i = threadIdx.x; i < 1024; i += RT) (&h[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t *mine = h[threadIdx.x & 3];
+    const uint64_t n16 = n / 16, stride = (uint64_t)gridDim.x * RT;
+    const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
+    for (uint64_t i = (uint64_t)blockIdx.x * RT + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = in4[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            // runs of equal indices are common in palette images: merge a word of four equal bytes into one add
+            const uint32_t b0 = w[k] & 255u;
+            if (w[k] == b0 * 0x01010101u) {
+                atomicAdd(&mine[b0], 4u);
+            } else {
+                atomicAdd(&mine[b0], 1u);
+                atomicAdd(&mine[(w[k] >> 8) & 255u], 1u);
+                atomicAdd(&mine[(w[k] >> 16) & 255u], 1u);
+                atomicAdd(&mine[w[k] >> 24], 1u);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (uint64_t i = n16 * 16; i < n; i++) atomicAdd(&mine[in[i]], 1u);
+    __syncthreads();
+    const uint32_t c = h[0][threadIdx.x] + h[1][threadIdx.x] + h[2][threadIdx.x] + h[3][threadIdx.x];
+    if (c) atomicAdd(&st->hist[threadIdx.x], (unsigned long long)c);
+}
+
+// byte -> byte look-up-table remap (palette.rs:43,121,183), 16 bytes per thread
+__global__ void __launch_bounds__(RT) k_lut(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint64_t n,
+                                             const uint8_t *__restrict__ lut_g) {
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = lut_g[threadIdx.x];
+    __syncthreads();
+    const uint64_t n16 = n / 16, stride = (uint64_t)gridDim.x * RT;
+    const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
+    uint4 *out4 = reinterpret_cast<uint4 *>(out);
+    for (uint64_t i = (uint64_t)blockIdx.x * RT + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = in4[i];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            w[k] = lut[w[k] & 255u] | (lut[(w[k] >> 8) & 255u] << 8) | (lut[(w[k] >> 16) & 255u] << 16) |
+                   (lut[w[k] >> 24] << 24);
+        out4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (uint64_t i = n16 * 16; i < n; i++) out[i] = lut[in[i]];
+}
+
+// most_popular_edge_color counts (palette.rs:198-204): first and last byte of every scanline of >= 2 bytes
+__global__ void __launch_bounds__(RT) k_edge_counts(const uint8_t *__restrict__ in, Geom g, ScanState *st) {
+    const uint32_t stride = gridDim.x * RT;
+    for (uint32_t r = blockIdx.x * RT + threadIdx.x; r < g.total_rows; r += stride) {
+        const PassDesc pd = g.pass[find_pass(g, r)];
+        if (pd.len < 2) continue;
+        const uint8_t *row = in + pd.in_base + (uint64_t)(r - pd.row0) * pd.len;
+        atomicAdd(&st->counts[row[0]], 1u);
+        atomicAdd(&st->counts[row[pd.len - 1]], 1u);
+    }
+}
+
+// CoOccurrenceMatrix::build counting (palette.rs:556-577).  One thread per 16-byte segment of a scanline; equal
+// consecutive (from,to) pairs are merged before they hit the matrix (flat regions are the common case).
+// `m` is n*n u32 in global memory (L2 resident, <= 256 KB).
+__global__ void __launch_bounds__(RT) k_cooccurrence(const uint8_t *__restrict__ in, Geom g, uint32_t n, uint32_t *m,
+                                                      ScanState *st) {
+    // work item = (row, segment); rows of different passes have different segment counts, so walk pass by pass
+    uint64_t base_item = 0;
+    const uint64_t tid = (uint64_t)blockIdx.x * RT + threadIdx.x, stride = (uint64_t)gridDim.x * RT;
+    for (uint32_t p = 0; p < g.n_pass; p++) {
+        const PassDesc pd = g.pass[p];
+        const uint32_t segs = (pd.len + 15) / 16;
+        const uint64_t items = (uint64_t)pd.nrows * segs;
+        // first item of this pass owned by this thread
+        uint64_t it = tid >= base_item % stride ? tid - base_item % stride : tid + stride - base_item % stride;
+        for (; it < items; it += stride) {
+            const uint32_t k = (uint32_t)(it / segs), seg = (uint32_t)(it % segs);
+            const uint8_t *row = in + pd.in_base + (uint64_t)k * pd.len;
+            // previous scanline in stream order, also across passes (palette.rs:566-575)
+            const uint8_t *prow = nullptr;
+            uint32_t plen = 0;
+            if (k > 0) { prow = row - pd.len; plen = pd.len; }
+            else if (p > 0) {
+                const PassDesc pp = g.pass[p - 1];
+                prow = in + pp.in_base + (uint64_t)(pp.nrows - 1) * pp.len;
+                plen = pp.len;
+            }
+            const uint32_t i0 = seg * 16, i1 = min(i0 + 16, pd.len);
+            uint32_t hk = 0xFFFFFFFFu, hc = 0, vk = 0xFFFFFFFFu, vc = 0;
+            uint32_t left = i0 ? row[i0 - 1] : 0xFFFFFFFFu;
+            for (uint32_t i = i0; i < i1; i++) {
+                const uint32_t val = row[i];
+                if (val >= n) { st->fail = 1; left = val; continue; }
+                if (left != 0xFFFFFFFFu && left < n) {
+                    const uint32_t key = left * n + val;
+                    if (key == hk) hc++;
+                    else { if (hc) atomicAdd(&m[hk], hc); hk = key; hc = 1; }
+                }
+                if (prow && i < plen) {
+                    const uint32_t pvv = prow[i];
+                    if (pvv < n) {
+                        const uint32_t key = pvv * n + val;
+                        if (key == vk) vc++;
+                        else { if (vc) atomicAdd(&m[vk], vc); vk = key; vc = 1; }
+                    } else st->fail = 1;
+                }
+                left = val;
+            }
+            if (hc) atomicAdd(&m[hk], hc);
+            if (vc) atomicAdd(&m[vk], vc);
+        }
+        base_item += items;
+    }
+}
+// symmetrise (palette.rs:580-587): M[i][j] = M[j][i] = M[i][j] + M[j][i]; the diagonal doubles
+__global__ void k_symmetrise(uint32_t *m, uint32_t n) {
+    const uint32_t i = blockIdx.x, j = threadIdx.x;
+    if (i >= n || j > i) return;
+    const uint32_t a = m[i * n + j], b = m[j * n + i];
+    const uint32_t s = (i == j) ? a + a : a + b;
+    m[i * n + j] = s;
+    m[j * n + i] = s;
+}
+
+// ---- host-side call scaffolding -------------------------------------------------------------------------------------------
+
+struct Call {
+    DeviceCtx *c = nullptr;
+    Slot *s = nullptr;
+    int err = 0;
+    ScanState *st = nullptr; // device
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    uint8_t *extra = nullptr; // scratch after ScanState (tables, LUTs)
+
+    Call(const uint8_t *data, size_t len, size_t out_cap, size_t extra_bytes = 0) {
+        c = current_ctx(&err);
+        if (!c) return;
+        s = acquire_slot(c);
+        if (!s) { err = fail(OXI_E_CUDA, "cannot create stream"); return; }
+        cudaError_t e = grow(&s->d_in, &s->in_cap, len + 64);
+        if (e == cudaSuccess) e = grow(&s->d_out, &s->out_cap, out_cap + 64);
+        if (e == cudaSuccess) e = grow(&s->scratch, &s->scratch_bytes, sizeof(ScanState) + extra_bytes + 256);
+        if (e != cudaSuccess) { err = fail_cuda(e, "cudaMalloc"); return; }
+        d_in = s->d_in;
+        d_out = s->d_out;
+        st = reinterpret_cast<ScanState *>(s->scratch);
+        extra = s->scratch + ((sizeof(ScanState) + 255) & ~(size_t)255);
+        e = cudaMemsetAsync(st, 0, sizeof(ScanState), s->stream);
+        if (e == cudaSuccess && len) e = cudaMemcpyAsync(d_in, data, len, cudaMemcpyHostToDevice, s->stream);
+        if (e != cudaSuccess) err = fail_cuda(e, "upload");
+    }
+    ~Call() {
+        if (s) {
+            cudaStreamSynchronize(s->stream);
+            release_slot(c, s);
+        }
+    }
+    bool ok() const { return err == 0; }
+    int state(ScanState *h) {
+        cudaError_t e = cudaMemcpyAsync(h, st, sizeof(ScanState), cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        return e == cudaSuccess ? 0 : fail_cuda(e, "download scan state");
+    }
+    int download(uint8_t *out, size_t n) {
+        cudaError_t e = n ? cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, s->stream) : cudaSuccess;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        return e == cudaSuccess ? 0 : fail_cuda(e, "download");
+    }
+    int check(const char *what) {
+        cudaError_t e = cudaGetLastError();
+        count_launch();
+        return e == cudaSuccess ? 0 : fail_cuda(e, what);
+    }
+};
+
+bool has_alpha(uint8_t ct) { return ct == 4 || ct == 6; }
+size_t byte_depth(const oxi_ihdr *h) { return h->bit_depth == 16 ? 2 : 1; }
+
+// rows of the image with a per-pass output row length chosen by `out_len_of(pass)`
+template <typename F>
+bool make_row_map(const Geom &g, F out_len_of, RowMap *m) {
+    memset(m, 0, sizeof *m);
+    m->n_pass = g.n_pass;
+    uint64_t ob = 0;
+    for (uint32_t p = 0; p < g.n_pass; p++) {
+        m->in_len[p] = g.pass[p].len;
+        m->nrows[p] = g.pass[p].nrows;
+        m->pixels[p] = g.pass[p].pixels;
+        m->in_base[p] = g.pass[p].in_base;
+        m->out_len[p] = out_len_of(g.pass[p]);
+        m->out_base[p] = ob;
+        m->out_items[p] = ob;
+        ob += (uint64_t)m->nrows[p] * m->out_len[p];
+    }
+    for (uint32_t p = g.n_pass; p < 8; p++) m->out_items[p] = ob;
+    return true;
+}
+
+void copy_aux(oxi_color_aux *dst, const oxi_color_aux *src) {
+    if (!dst) return;
+    if (src) *dst = *src;
+    else memset(dst, 0, sizeof *dst);
+}
+
+// LUT remap of a device-resident image already uploaded by `call`
+int run_lut(Call &call, size_t len, const uint8_t lut[256]) {
+    cudaError_t e = cudaMemcpyAsync(call.extra, lut, 256, cudaMemcpyHostToDevice, call.s->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "upload LUT");
+    k_lut<<<grid_for((len + 15) / 16, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, len, call.extra);
+    return call.check("k_lut");
+}
+
+int32_t luma_key(const uint8_t *c) { // palette.rs:92-105
+    const int32_t a = c[3];
+    return ((a & 0xFE) << 18) + (a & 0x01) - (int32_t)c[0] * 299 - (int32_t)c[1] * 587 - (int32_t)c[2] * 114;
+}
+
+} // namespace
+} // namespace oxi
+
+using namespace oxi;
+
+extern "C" {
+
+int oxi_cleaned_alpha_channel(const oxi_ihdr *h, const uint8_t *data, size_t len, uint8_t *out) {
+    if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
+    if (!has_alpha(h->color_type)) return OXI_NONE; // alpha.rs:12-14
+    const uint32_t bd = (uint32_t)byte_depth(h), bpp = (uint32_t)channels(h->color_type) * bd, cb = bpp - bd;
+    const size_t used = len / bpp * bpp; // chunks_exact
+    Call call(data, len, len);
+    if (!call.ok()) return call.err;
+    const uint64_t n16 = used / 16;
+    k_clean_alpha<<<grid_for(n16 ? n16 : 1, call.c->num_sms), RT, 0, call.s->stream>>>(
+        reinterpret_cast<const uint4 *>(call.d_in), reinterpret_cast<uint4 *>(call.d_out), n16, call.d_in + n16 * 16,
+        call.d_out + n16 * 16, (uint32_t)(used - n16 * 16), bpp, cb);
+    if (int rc = call.check("k_clean_alpha")) return rc;
+    return call.download(out, used);
+}
+
+int oxi_reduced_alpha_channel(const oxi_ihdr *h, const uint8_t *data, size_t len, int optimize_alpha, uint8_t *out,
+                              size_t *out_len, oxi_ihdr *oh, oxi_color_aux *oaux) {
+    if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
+    if (!has_alpha(h->color_type)) return OXI_NONE;
+    const uint32_t bd = (uint32_t)byte_depth(h), bpp = (uint32_t)channels(h->color_type) * bd, cb = bpp - bd;
+    const uint64_t npix = len / bpp;
+    Call call(data, len, npix * cb);
+    if (!call.ok()) return call.err;
+    k_alpha_scan<<<grid_for(npix, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, npix, bpp, cb, optimize_alpha, call.st);
+    if (int rc = call.check("k_alpha_scan")) return rc;
+    ScanState st;
+    if (int rc = call.state(&st)) return rc;
+    if (st.fail) return OXI_NONE; // partially transparent pixel (alpha.rs:53-55)
+    int trns = -1;
+    if (st.has_transparency) { // alpha.rs:62-75
+        auto used = [&](int v) { return (st.used[v >> 5] >> (v & 31)) & 1u; };
+        if (h->color_type == 4) {
+            const int tries[4] = {0x00, 0xFF, 0x55, 0xAA};
+            for (int k = 0; k < 4 && trns < 0; k++)
+                if (!used(tries[k])) trns = tries[k];
+        }
+        for (int v = 0; v < 256 && trns < 0; v++)
+            if (!used(v)) trns = v;
+        if (trns < 0) return OXI_NONE;
+    }
+    k_alpha_strip<<<grid_for(npix, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, npix, bpp, cb, trns);
+    if (int rc = call.check("k_alpha_strip")) return rc;
+    if (int rc = call.download(out, npix * cb)) return rc;
+    if (out_len) *out_len = npix * cb;
+    if (oh) { *oh = *h; oh->color_type = h->color_type == 4 ? 0 : 2; }
+    if (oaux) {
+        memset(oaux, 0, sizeof *oaux);
+        if (trns >= 0) { // alpha.rs:88-91
+            const uint16_t t = h->bit_depth == 16 ? (uint16_t)((trns << 8) | trns) : (uint16_t)trns;
+            oaux->has_trns = 1;
+            oaux->trns[0] = oaux->trns[1] = oaux->trns[2] = t;
+        }
+    }
+    return OXI_OK;
+}
+
+int oxi_reduced_bit_depth_16_to_8(const oxi_ihdr *h, const uint8_t *data, size_t len, int force_scale, uint8_t *out,
+                                  size_t *out_len, oxi_ihdr *oh) {
+    if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
+    if (h->bit_depth != 16) return OXI_NONE;
+    const uint64_t ns = len / 2;
+    Call call(data, len, ns);
+    if (!call.ok()) return call.err;
+    k_16to8<<<grid_for((ns + 7) / 8, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, ns, force_scale ? 1 : 0,
+                                                                                 call.st);
+    if (int rc = call.check("k_16to8")) return rc;
+    if (!force_scale) {
+        ScanState st;
+        if (int rc = call.state(&st)) return rc;
+        if (st.fail) return OXI_NONE; // some sample has hi != lo (bit_depth.rs:19-22)
+    }
+    if (int rc = call.download(out, ns)) return rc;
+    if (out_len) *out_len = ns;
+    if (oh) { *oh = *h; oh->bit_depth = 8; }
+    return OXI_OK;
+}
+
+int oxi_reduced_bit_depth_8_or_less(const oxi_ihdr *h, const oxi_color_aux *aux, const uint8_t *data, size_t len,
+                                    uint8_t *out, size_t *out_len, oxi_ihdr *oh, oxi_color_aux *oaux) {
+    if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
+    if (h->bit_depth != 8 || channels(h->color_type) != 1) return OXI_NONE;
+    Geom g;
+    if (!build_geom(h, len, 0, &g)) return fail(OXI_E_ARG, "invalid IHDR");
+    Call call(data, len, len);
+    if (!call.ok()) return call.err;
+    uint32_t bits;
+    if (h->color_type == 3) { // bit_depth.rs:73-80
+        const uint32_t n = aux ? aux->n_palette : 0;
+        if (n <= 2) bits = 1;
+        else if (n <= 4) bits = 2;
+        else if (n <= 16) bits = 4;
+        else return OXI_NONE;
+    } else {
+        k_min_bits<<<grid_for((len + 15) / 16, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, len, call.st);
+        if (int rc = call.check("k_min_bits")) return rc;
+        ScanState st;
+        if (int rc = call.state(&st)) return rc;
+        bits = st.max_bits ? st.max_bits : 1;
+        if (bits >= 8) return OXI_NONE;
+    }
+    const uint32_t per = 8 / bits;
+    RowMap m;
+    make_row_map(g, [per](const PassDesc &pd) { return (pd.len + per - 1) / per; }, &m);
+    const uint64_t total = m.out_items[g.n_pass];
+    k_pack_bits<<<grid_for(total, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, m, bits);
+    if (int rc = call.check("k_pack_bits")) return rc;
+    if (int rc = call.download(out, total)) return rc;
+    if (out_len) *out_len = total;
+    if (oh) { *oh = *h; oh->bit_depth = (uint8_t)bits; }
+    if (oaux) {
+        copy_aux(oaux, aux);
+        if (h->color_type == 0 && aux && aux->has_trns) { // bit_depth.rs:134-153
+            const uint16_t trans = aux->trns[0];
+            const uint16_t reduced = (uint16_t)((trans & 0xFF) >> (8 - bits));
+            uint16_t check = reduced;
+            for (uint32_t b = bits; b < 8; b <<= 1) check = (uint16_t)((check << b) | check);
+            oaux->has_trns = trans == check;
+            oaux->trns[0] = trans == check ? reduced : 0;
+        }
+    }
+    return OXI_OK;
+}
+
+int oxi_expanded_bit_depth_to_8(const oxi_ihdr *h, const oxi_color_aux *aux, const uint8_t *data, size_t len, uint8_t *out,
+                                size_t *out_len, oxi_ihdr *oh, oxi_color_aux *oaux) {
+    if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
+    const uint32_t depth = h->bit_depth;
+    if (depth >= 8) return OXI_NONE;
+    Geom g;
+    if (!build_geom(h, len, 0, &g)) return fail(OXI_E_ARG, "invalid IHDR");
+    RowMap m;
+    make_row_map(g, [](const PassDesc &pd) { return pd.pixels; }, &m);
+    const uint64_t total = m.out_items[g.n_pass];
+    Call call(data, len, total);
+    if (!call.ok()) return call.err;
+    k_expand_bits<<<grid_for(total, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, m, depth,
+                                                                               h->color_type == 0);
+    if (int rc = call.check("k_expand_bits")) return rc;
+    if (int rc = call.download(out, total)) return rc;
+    if (out_len) *out_len = total;
+    if (oh) { *oh = *h; oh->bit_depth = 8; }
+    if (oaux) {
+        copy_aux(oaux, aux);
+        if (h->color_type == 0 && aux && aux->has_trns) { // bit_depth.rs:206-220
+            uint16_t trans = aux->trns[0];
+            for (uint32_t b = depth; b < 8; b <<= 1) trans = (uint16_t)((trans << b) | trans);
+            oaux->trns[0] = trans;
+        }
+    }
+    return OXI_OK;
+}
+
+int oxi_reduced_rgb_to_grayscale(const oxi_ihdr *h, const oxi_color_aux *aux, const uint8_t *data, size_t len, uint8_t *out,
+                                 size_t *out_len, oxi_ihdr *oh, oxi_color_aux *oaux) {
+    if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
+    if (h->color_type != 2 && h->color_type != 6) return OXI_NONE;
+    const uint32_t bd = (uint32_t)byte_depth(h), bpp = (uint32_t)channels(h->color_type) * bd, keep = bpp - 2 * bd;
+    const uint64_t npix = len / bpp;
+    Call call(data, len, npix * keep);
+    if (!call.ok()) return call.err;
+    k_rgb_to_gray<<<grid_for(npix, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, npix, bpp, bd, call.st);
+    if (int rc = call.check("k_rgb_to_gray")) return rc;
+    ScanState st;
+    if (int rc = call.state(&st)) return rc;
+    if (st.fail) return OXI_NONE;
+    if (int rc = call.download(out, npix * keep)) return rc;
+    if (out_len) *out_len = npix * keep;
+    if (oh) { *oh = *h; oh->color_type = h->color_type == 2 ? 0 : 4; }
+    if (oaux) {
+        memset(oaux, 0, sizeof *oaux);
+        if (h->color_type == 2 && aux && aux->has_trns && aux->trns[0] == aux->trns[1] && aux->trns[1] == aux->trns[2]) {
+            oaux->has_trns = 1; // color.rs:120-128
+            oaux->trns[0] = aux->trns[0];
+        }
+    }
+    return OXI_OK;
+}
+
+int oxi_reduced_to_indexed(const oxi_ihdr *h, const oxi_color_aux *aux, const uint8_t *data, size_t len, int allow_grayscale,
+                           uint8_t *out, size_t *out_len, oxi_ihdr *oh, oxi_color_aux *oaux) {
+    if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
+    if (h->bit_depth != 8 || h->color_type == 3) return OXI_NONE; // color.rs:39-44
+    const bool gray = h->color_type == 0 || h->color_type == 4;
+    if (!allow_grayscale && gray) return OXI_NONE;
+    const uint32_t ch = (uint32_t)channels(h->color_type);
+    const uint64_t npix = len / ch;
+    Call call(data, len, npix, sizeof(ColorTable));
+    if (!call.ok()) return call.err;
+    ColorTable *tab = reinterpret_cast<ColorTable *>(call.extra);
+    cudaError_t e = cudaMemsetAsync(tab->key, 0, sizeof tab->key, call.s->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(tab->first, 0xFF, sizeof tab->first, call.s->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "memset colour table");
+    if (npix) {
+        k_collect_colors<<<grid_for(npix, call.c->num_sms, 4), RT, 0, call.s->stream>>>(call.d_in, npix, ch, tab, call.st);
+        if (int rc = call.check("k_collect_colors")) return rc;
+    }
+    ScanState st;
+    if (int rc = call.state(&st)) return rc;
+    if (st.overflow || st.n_distinct > 256) return OXI_NONE; // 257th distinct colour (color.rs:29-31)
+    std::vector<unsigned long long> keys(GSLOTS), first(GSLOTS);
+    e = cudaMemcpyAsync(keys.data(), tab->key, sizeof tab->key, cudaMemcpyDeviceToHost, call.s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(first.data(), tab->first, sizeof tab->first, cudaMemcpyDeviceToHost, call.s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(call.s->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "download colour table");
+    std::vector<uint32_t> slots;
+    for (uint32_t s = 0; s < GSLOTS; s++)
+        if (keys[s]) slots.push_back(s);
+    std::sort(slots.begin(), slots.end(), [&](uint32_t a, uint32_t b) { return first[a] < first[b]; }); // insertion order
+    std::vector<uint32_t> index(GSLOTS, 0);
+    for (size_t i = 0; i < slots.size(); i++) index[slots[i]] = (uint32_t)i;
+    e = cudaMemcpyAsync(tab->index, index.data(), sizeof tab->index, cudaMemcpyHostToDevice, call.s->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "upload palette indices");
+    if (npix) {
+        const size_t smem = GSLOTS * 8 + GSLOTS;
+        cudaFuncSetAttribute((const void *)k_index_colors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_index_colors<<<grid_for(npix, call.c->num_sms, 4), RT, smem, call.s->stream>>>(call.d_in, call.d_out, npix, ch, tab);
+        if (int rc = call.check("k_index_colors")) return rc;
+    }
+    if (int rc = call.download(out, npix)) return rc;
+    if (out_len) *out_len = npix;
+    if (oh) { *oh = *h; oh->color_type = 3; }
+    if (oaux) {
+        memset(oaux, 0, sizeof *oaux);
+        oaux->n_palette = (uint32_t)slots.size();
+        for (size_t i = 0; i < slots.size(); i++) {
+            const uint32_t key = (uint32_t)keys[slots[i]];
+            const uint8_t c0 = key & 255, c1 = (key >> 8) & 255, c2 = (key >> 16) & 255, c3 = key >> 24;
+            uint8_t *p = oaux->palette[i];
+            switch (h->color_type) {
+            case 0: { // color.rs:51-62
+                const bool t = aux && aux->has_trns && (uint8_t)aux->trns[0] == c0;
+                p[0] = p[1] = p[2] = c0; p[3] = t ? 0 : 255;
+                break;
+            }
+            case 2: { // color.rs:64-77
+                const bool t = aux && aux->has_trns && (uint8_t)aux->trns[0] == c0 && (uint8_t)aux->trns[1] == c1 &&
+                               (uint8_t)aux->trns[2] == c2;
+                p[0] = c0; p[1] = c1; p[2] = c2; p[3] = t ? 0 : 255;
+                break;
+            }
+            case 4: p[0] = p[1] = p[2] = c0; p[3] = c1; break;
+            default: p[0] = c0; p[1] = c1; p[2] = c2; p[3] = c3; break;
+            }
+        }
+    }
+    return OXI_OK;
+}
+
+int oxi_used_histogram256(const uint8_t *data, size_t len, uint64_t hist[256]) {
+    if (!data || !hist) return fail(OXI_E_ARG, "bad arguments");
+    Call call(data, len, 0);
+    if (!call.ok()) return call.err;
+    k_hist256<<<grid_for((len + 15) / 16, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, len, call.st);
+    if (int rc = call.check("k_hist256")) return rc;
+    ScanState st;
+    if (int rc = call.state(&st)) return rc;
+    for (int i = 0; i < 256; i++) hist[i] = st.hist[i];
+    return OXI_OK;
+}
+
+int oxi_lut_remap(const uint8_t *data, size_t len, const uint8_t lut[256], uint8_t *out) {
+    if (!data || !out || !lut) return fail(OXI_E_ARG, "bad arguments");
+    Call call(data, len, len, 256);
+    if (!call.ok()) return call.err;
+    if (int rc = run_lut(call, len, lut)) return rc;
+    return call.download(out, len);
+}
+
+int oxi_edge_color_counts(const oxi_ihdr *h, const uint8_t *data, size_t len, uint32_t counts[256]) {
+    Geom g;
+    if (!data || !counts || !build_geom(h, len, 0, &g)) return fail(OXI_E_ARG, "bad arguments");
+    Call call(data, len, 0);
+    if (!call.ok()) return call.err;
+    k_edge_counts<<<grid_for(g.total_rows, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, g, call.st);
+    if (int rc = call.check("k_edge_counts")) return rc;
+    ScanState st;
+    if (int rc = call.state(&st)) return rc;
+    memcpy(counts, st.counts, sizeof st.counts);
+    return OXI_OK;
+}
+
+int oxi_reduced_palette(const oxi_ihdr *h, const oxi_color_aux *aux, const uint8_t *data, size_t len, int optimize_alpha,
+                        uint8_t *out, oxi_color_aux *oaux) {
+    if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
+    if (h->bit_depth != 8 || h->color_type != 3 || !aux) return OXI_NONE; // palette.rs:13-18
+    Call call(data, len, len, 256);
+    if (!call.ok()) return call.err;
+    k_hist256<<<grid_for((len + 15) / 16, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, len, call.st);
+    if (int rc = call.check("k_hist256")) return rc;
+    ScanState st;
+    if (int rc = call.state(&st)) return rc;
+    uint8_t condensed[256][4], byte_map[256];
+    uint32_t nc = 0;
+    bool did_change = false;
+    memset(byte_map, 0, sizeof byte_map);
+    for (int i = 0; i < 256; i++) { // palette.rs:28-39
+        if (!st.hist[i]) continue;
+        uint8_t c[4] = {0, 0, 0, 255}; // indices beyond the palette are opaque black
+        if ((uint32_t)i < aux->n_palette) memcpy(c, aux->palette[i], 4);
+        if (optimize_alpha && c[3] == 0) c[0] = c[1] = c[2] = 0; // add_color_to_set, palette.rs:64-73
+        uint32_t idx = nc;
+        for (uint32_t k = 0; k < nc; k++)
+            if (!memcmp(condensed[k], c, 4)) { idx = k; break; }
+        if (idx == nc) memcpy(condensed[nc++], c, 4);
+        byte_map[i] = (uint8_t)idx;
+        did_change |= idx != (uint32_t)i;
+    }
+    if (did_change) { // palette.rs:41-43
+        if (int rc = run_lut(call, len, byte_map)) return rc;
+        if (int rc = call.download(out, len)) return rc;
+    } else if (nc != aux->n_palette) { // palette.rs:44-47: data unchanged, palette resized
+        memcpy(out, data, len);
+    } else {
+        return OXI_NONE;
+    }
+    if (oaux) {
+        memset(oaux, 0, sizeof *oaux);
+        oaux->n_palette = nc;
+        memcpy(oaux->palette, condensed, (size_t)nc * 4);
+    }
+    return OXI_OK;
+}
+
+int oxi_sorted_palette(const oxi_ihdr *h, const oxi_color_aux *aux, const uint8_t *data, size_t len, uint8_t *out,
+                       oxi_color_aux *oaux) {
+    if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
+    if (h->bit_depth != 8 || h->color_type != 3 || !aux || aux->n_palette <= 1) return OXI_NONE; // palette.rs:78-84
+    Geom g;
+    if (!build_geom(h, len, 0, &g)) return fail(OXI_E_ARG, "invalid IHDR");
+    const uint32_t n = aux->n_palette > 256 ? 256 : aux->n_palette;
+    Call call(data, len, len, 256);
+    if (!call.ok()) return call.err;
+    k_edge_counts<<<grid_for(g.total_rows, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, g, call.st);
+    if (int rc = call.check("k_edge_counts")) return rc;
+    ScanState st;
+    if (int rc = call.state(&st)) return rc;
+    // most_popular_edge_color, palette.rs:205-216: last maximum among the first n bins, None when not unique over all 256
+    uint32_t best = 0;
+    for (uint32_t i = 0; i < n; i++)
+        if (st.counts[i] >= st.counts[best]) best = i;
+    int equal = 0;
+    for (int i = 0; i < 256; i++) equal += st.counts[i] == st.counts[best];
+    const int keep_first = equal > 1 ? -1 : (int)best;
+    std::vector<uint32_t> order;
+    for (uint32_t i = 0; i < n; i++)
+        if ((int)i != keep_first) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        return luma_key(aux->palette[a]) < luma_key(aux->palette[b]);
+    });
+    if (keep_first >= 0) order.insert(order.begin(), (uint32_t)keep_first);
+    bool identity = true;
+    for (uint32_t i = 0; i < n; i++) identity &= order[i] == i;
+    if (identity) return OXI_NONE;
+    uint8_t byte_map[256];
+    memset(byte_map, 0, sizeof byte_map);
+    for (uint32_t i = 0; i < n; i++) byte_map[order[i]] = (uint8_t)i;
+    if (int rc = run_lut(call, len, byte_map)) return rc;
+    if (int rc = call.download(out, len)) return rc;
+    if (oaux) {
+        memset(oaux, 0, sizeof *oaux);
+        oaux->n_palette = n;
+        for (uint32_t i = 0; i < n; i++) memcpy(oaux->palette[i], aux->palette[order[i]], 4);
+    }
+    return OXI_OK;
+}
+
+int oxi_apply_palette_reorder(const oxi_ihdr *h, const oxi_color_aux *aux, const uint32_t *remapping, const uint8_t *data,
+                              size_t len, uint8_t *out, oxi_color_aux *oaux) {
+    if (!valid_ihdr(h) || !data || !out || !remapping) return fail(OXI_E_ARG, "bad arguments");
+    if (h->color_type != 3 || !aux) return OXI_NONE;
+    const uint32_t n = aux->n_palette > 256 ? 256 : aux->n_palette;
+    bool identity = true;
+    for (uint32_t i = 0; i < n; i++) identity &= remapping[i] == i;
+    if (identity) return OXI_NONE; // palette.rs:171-175
+    uint8_t byte_map[256];
+    memset(byte_map, 0, sizeof byte_map);
+    oxi_color_aux na;
+    memset(&na, 0, sizeof na);
+    na.n_palette = n;
+    for (uint32_t i = 0; i < n; i++) {
+        if (remapping[i] >= n) return fail(OXI_E_ARG, "remapping entry beyond the palette");
+        memcpy(na.palette[i], aux->palette[remapping[i]], 4);
+        byte_map[remapping[i]] = (uint8_t)i;
+    }
+    Call call(data, len, len, 256);
+    if (!call.ok()) return call.err;
+    if (int rc = run_lut(call, len, byte_map)) return rc;
+    if (int rc = call.download(out, len)) return rc;
+    if (oaux) *oaux = na;
+    return OXI_OK;
+}
+
+int oxi_cooccurrence_build(const oxi_ihdr *h, uint32_t n, const uint8_t *data, size_t len, uint32_t *matrix) {
+    Geom g;
+    if (!data || !matrix || n == 0 || n > 256 || !build_geom(h, len, 0, &g)) return fail(OXI_E_ARG, "bad arguments");
+    if (h->bit_depth != 8) return fail(OXI_E_ARG, "co-occurrence needs 8-bit indices");
+    const size_t mbytes = (size_t)n * n * 4;
+    Call call(data, len, 0, mbytes);
+    if (!call.ok()) return call.err;
+    uint32_t *m = reinterpret_cast<uint32_t *>(call.extra);
+    cudaError_t e = cudaMemsetAsync(m, 0, mbytes, call.s->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "memset matrix");
+    const uint64_t items = ((uint64_t)g.data_len + 15) / 16 + g.total_rows;
+    k_cooccurrence<<<grid_for(items, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, g, n, m, call.st);
+    if (int rc = call.check("k_cooccurrence")) return rc;
+    k_symmetrise<<<n, 256, 0, call.s->stream>>>(m, n);
+    if (int rc = call.check("k_symmetrise")) return rc;
+    ScanState st;
+    if (int rc = call.state(&st)) return rc;
+    if (st.fail) return fail(OXI_E_ARG, "pixel index beyond the palette (run reduced_palette first, palette.rs:533-536)");
+    e = cudaMemcpyAsync(matrix, m, mbytes, cudaMemcpyDeviceToHost, call.s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(call.s->stream);
+    return e == cudaSuccess ? OXI_OK : fail_cuda(e, "download matrix");
+}
+
+} // extern "C"
