@@ -29,7 +29,8 @@ namespace {
 constexpr int SC_MINSUM = 1, SC_ENTROPY = 2, SC_BIGRAM = 4;
 constexpr int HIST_REP = 4;      // copies of each Entropy histogram (lane & 3) to thin same-address atomics
 constexpr uint32_t PAD = 32;     // zero bytes in front of every staged row (left/upleft of the first pixel)
-constexpr uint32_t SMEM_HDR = 512;
+constexpr uint32_t SMEM_HDR = 1536;
+constexpr int OUT_LIST = 64;         // outlier bigrams per trial that are resolved by one warp instead of the big table
 constexpr uint32_t SMEM_LIMIT = 232448; // 227 KB
 
 struct FastParams {
@@ -152,6 +153,12 @@ __device__ __forceinline__ uint32_t residual_at(int f, const uint8_t *cur, const
     return residual_byte(f, cur[i], cur[i - bpp], up[i], up[i - bpp]);
 }
 
+// Bigram tables are indexed by (first byte, second byte) with two u16 counters per 32-bit word.  The word index is
+// XOR-swizzled with the first byte so that the bank depends on both bytes: runs like "(x, 0)" (every pixel's alpha
+// residual) would otherwise put a whole warp on one bank.
+__device__ __forceinline__ uint32_t big_word(uint32_t bg) { return (bg >> 1) ^ ((bg >> 8) & 31u); }
+__device__ __forceinline__ uint32_t small_word(uint32_t idx) { return (idx >> 1) ^ ((idx >> 6) & 31u); }
+
 // ---- shared-memory carve-up --------------------------------------------------------------------------------------
 struct Smem {
     uint64_t *bar;     // 3 mbarriers
@@ -164,6 +171,7 @@ struct Smem {
     uint32_t *table;   // 32768 words = 65536 u16 counters
     uint32_t *small;   // [5][2048] words = five 64x64 u16 counter tables (in-range bigrams), optional
     uint32_t *s_out;   // [5] outlier-window count per trial
+    uint16_t *s_list;  // [5][OUT_LIST] outlier bigrams of trials with few of them
 };
 template <int SC>
 __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb) {
@@ -171,6 +179,7 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb) {
     s.bar = reinterpret_cast<uint64_t *>(base);
     uint32_t *u = reinterpret_cast<uint32_t *>(base + 64);
     s.s_min = u; s.s_ent = u + 8; s.s_bgc = u + 16; s.s_bge = u + 24; s.s_out = u + 32;
+    s.s_list = reinterpret_cast<uint16_t *>(base + 768);
     s.rows = base + SMEM_HDR;
     uint8_t *p = s.rows + 3 * (size_t)rb;
     s.hist = reinterpret_cast<uint32_t *>(p);
@@ -320,7 +329,7 @@ __device__ __forceinline__ void bigram_trial(const uint8_t *cur, const uint8_t *
             const uint32_t bg = (prev << 8) | b;
             prev = b;
             if (j < valid) {
-                const uint32_t old = atomicAdd(&table[bg >> 1], (bg & 1u) ? 0x10000u : 1u);
+                const uint32_t old = atomicAdd(&table[big_word(bg)], (bg & 1u) ? 0x10000u : 1u);
                 const uint32_t cnt = (bg & 1u) ? (old >> 16) : (old & 0xFFFFu);
                 if (cnt == 0) own |= 1ull << (4 * i + j);
             }
@@ -338,8 +347,8 @@ __device__ __forceinline__ void bigram_trial(const uint8_t *cur, const uint8_t *
                 const uint32_t bg = (prev << 8) | b;
                 prev = b;
                 if ((own >> (4 * i + j)) & 1ull) {
-                    const uint32_t cnt = t16[bg];
-                    t16[bg] = 0;
+                    const uint32_t cnt = t16[(big_word(bg) << 1) | (bg & 1u)];
+                    t16[(big_word(bg) << 1) | (bg & 1u)] = 0;
                     distinct += 1;
                     ent += ilog2i(cnt);
                 }
@@ -420,21 +429,48 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
                 if (j < valid) {
                     if (((tp | tj) & 0xC0u) == 0) {
                         const uint32_t idx = (tp << 6) | tj;
-                        atomicAdd(&tab[idx >> 1], (idx & 1u) ? 0x10000u : 1u);
+                        atomicAdd(&tab[small_word(idx)], (idx & 1u) ? 0x10000u : 1u);
                     } else {
                         om[f] |= 1u << (4 * i + j);
+                        // claim a slot in the trial's short outlier list (the count keeps growing past the list size)
+                        // (once the count has passed the list size nobody needs to add any more: "many" is enough)
+                        if (*(volatile uint32_t *)&sm.s_out[f] <= (uint32_t)OUT_LIST) {
+                            const uint32_t slot = atomicAdd(&sm.s_out[f], 1u);
+                            if (slot < (uint32_t)OUT_LIST)
+                                sm.s_list[f * OUT_LIST + slot] = (uint16_t)((((tp + 224u) & 255u) << 8) | ((tj + 224u) & 255u));
+                        }
                     }
                 }
                 tp = tj;
             }
         }
     }
-#pragma unroll
-    for (int f = 0; f < 5; f++) {
-        const uint32_t n = warp_sum((uint32_t)__popc(om[f]));
-        if ((threadIdx.x & 31) == 0 && n) atomicAdd(&sm.s_out[f], n);
-    }
     __syncthreads();
+    // trials with only a few outliers: warp f dedupes the list of trial f by brute force (no table, no barrier)
+    if ((threadIdx.x >> 5) < 5) {
+        const int f = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const uint32_t n = sm.s_out[f];
+        if (n > 0 && n <= (uint32_t)OUT_LIST) {
+            uint32_t dis = 0, ent = 0;
+            for (uint32_t e = lane; e < n; e += 32) {
+                const uint16_t me = sm.s_list[f * OUT_LIST + e];
+                uint32_t cnt = 0;
+                bool first = true;
+                for (uint32_t q = 0; q < n; q++) {
+                    const bool eq = sm.s_list[f * OUT_LIST + q] == me;
+                    cnt += eq;
+                    first &= !(eq && q < e);
+                }
+                if (first) { dis++; ent += ilog2i(cnt); }
+            }
+            dis = warp_sum(dis);
+            ent = warp_sum(ent);
+            if (lane == 0) {
+                atomicAdd(&sm.s_bgc[f], dis);
+                atomicAdd(&sm.s_bge[f], ent);
+            }
+        }
+    }
     // sweep the five dense tables
     {
         uint32_t dis[5] = {0, 0, 0, 0, 0}, ent[5] = {0, 0, 0, 0, 0};
@@ -463,7 +499,7 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
     uint16_t *t16 = reinterpret_cast<uint16_t *>(sm.table);
 #pragma unroll
     for (int f = 0; f < 5; f++) {
-        if (sm.s_out[f] == 0) continue; // uniform: written before the barrier above
+        if (sm.s_out[f] <= (uint32_t)OUT_LIST) continue; // uniform: final before the barrier above; few -> done by a warp
         uint32_t own = 0;
 #pragma unroll
         for (int i = 0; i < WPT; i++) {
@@ -474,7 +510,7 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
                 const uint32_t bg = (prev << 8) | b;
                 prev = b;
                 if ((om[f] >> (4 * i + j)) & 1u) {
-                    const uint32_t old = atomicAdd(&sm.table[bg >> 1], (bg & 1u) ? 0x10000u : 1u);
+                    const uint32_t old = atomicAdd(&sm.table[big_word(bg)], (bg & 1u) ? 0x10000u : 1u);
                     if (((bg & 1u) ? (old >> 16) : (old & 0xFFFFu)) == 0) own |= 1u << (4 * i + j);
                 }
             }
@@ -491,8 +527,8 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
                     const uint32_t bg = (prev << 8) | b;
                     prev = b;
                     if ((own >> (4 * i + j)) & 1u) {
-                        const uint32_t cnt = t16[bg];
-                        t16[bg] = 0;
+                        const uint32_t cnt = t16[(big_word(bg) << 1) | (bg & 1u)];
+                        t16[(big_word(bg) << 1) | (bg & 1u)] = 0;
                         distinct += 1;
                         ent += ilog2i(cnt);
                     }

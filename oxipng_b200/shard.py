@@ -1,0 +1,86 @@
+"""Multi-GPU sharding of the filter-search path.  No data-path collective exists or is needed:
+
+* by image: image i of a batch goes to one rank (contiguous, balanced shards);
+* by row band, for one very large image: with optimize_alpha off a filtered row depends only on its own bytes and the
+  previous *raw* row of the same pass (png/mod.rs:375-378,422), so a band needs a one-row halo and nothing else.  A band
+  is handed to the unchanged C ABI as a small non-interlaced image whose first row is the halo; that row's output is
+  dropped.  Outputs of the bands are disjoint, contiguous ranges of the filtered stream.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import numpy as np
+
+
+def image_shard(n_images: int, world: int, rank: int) -> tuple[int, int]:
+    """-> (first image, count) of `rank`'s contiguous shard; counts differ by at most one."""
+    base, extra = divmod(n_images, world)
+    start = rank * base + min(rank, extra)
+    return start, base + (1 if rank < extra else 0)
+
+
+@dataclass(frozen=True)
+class Band:
+    pass_index: int      # index into the image's non-empty passes (0 for non-interlaced)
+    width_px: int        # pixels per scanline of that pass
+    row_len: int         # bytes per scanline
+    first_row: int       # global scanline index of the band's first row
+    n_rows: int
+    has_halo: bool       # False when the band starts a pass (previous row = zeros)
+    in_begin: int        # byte range of PngImage.data to ship, halo row included
+    in_end: int
+    out_begin: int       # byte range of the filtered stream this band produces
+    out_end: int
+
+
+def row_bands(scan_lines: Sequence[tuple], n_parts: int) -> List[Band]:
+    """Split an image (given as PngImage.scan_lines(): [(len, pass, pixels)]) into about n_parts bands of nearly equal
+    byte size that never cross a pass."""
+    passes = []  # (pass id, len, pixels, first row, nrows, in_base)
+    off = 0
+    for r, (ln, ps, px) in enumerate(scan_lines):
+        if not passes or passes[-1][0] != ps or passes[-1][1] != ln:
+            passes.append([ps, ln, px, r, 0, off])
+        passes[-1][4] += 1
+        off += ln
+    total = off
+    bands: List[Band] = []
+    for pi, (ps, ln, px, r0, nrows, in_base) in enumerate(passes):
+        share = max(1, round(n_parts * (nrows * ln) / max(total, 1)))
+        share = min(share, nrows)
+        for b in range(share):
+            k0, k1 = b * nrows // share, (b + 1) * nrows // share
+            if k1 <= k0:
+                continue
+            halo = k0 > 0
+            bands.append(Band(pi, px, ln, r0 + k0, k1 - k0, halo,
+                              in_base + (k0 - (1 if halo else 0)) * ln, in_base + k1 * ln,
+                              in_base + k0 * ln + r0 + k0, in_base + k1 * ln + r0 + k1))
+    return bands
+
+
+def filter_image_banded(png, strategy, n_parts: int, devices: Sequence[int] = (0,)):
+    """filter_image of one large image split into row bands, band b on devices[b % len(devices)].
+    optimize_alpha must be off (rows are serially dependent otherwise).  -> (filtered stream, filters_used)"""
+    from . import png as P
+    from ._lib import check, lib
+    lines = png.scan_lines()
+    bands = row_bands(lines, n_parts)
+    out = np.empty(png.data.size + len(lines), dtype=np.uint8)
+    used = np.empty(len(lines), dtype=np.uint8)
+    for bi, b in enumerate(bands):
+        check(lib().oxi_set_device(devices[bi % len(devices)]), "oxi_set_device")
+        rows = b.n_rows + (1 if b.has_halo else 0)
+        sub = P.PngImage(P.IhdrData(b.width_px, rows, png.ihdr.color_type, png.ihdr.bit_depth, False),
+                         png.data[b.in_begin:b.in_end])
+        strat = strategy
+        if strategy.kind == "Predefined":  # row i of the band is global row first_row + i
+            lines_ = list(strategy.lines[b.first_row:b.first_row + b.n_rows])
+            strat = P.FilterStrategy.Predefined(([0] if b.has_halo else []) + lines_)
+        o, u = P.filter_image_multi(sub, [strat], False)
+        skip = 1 if b.has_halo else 0
+        out[b.out_begin:b.out_end] = o[0][skip * (b.row_len + 1):]
+        used[b.first_row:b.first_row + b.n_rows] = u[0][skip:]
+    return out, used
