@@ -157,7 +157,10 @@ __device__ __forceinline__ uint32_t residual_at(int f, const uint8_t *cur, const
 // XOR-swizzled with the first byte so that the bank depends on both bytes: runs like "(x, 0)" (every pixel's alpha
 // residual) would otherwise put a whole warp on one bank.
 __device__ __forceinline__ uint32_t big_word(uint32_t bg) { return (bg >> 1) ^ ((bg >> 8) & 31u); }
-__device__ __forceinline__ uint32_t small_word(uint32_t idx) { return (idx >> 1) ^ ((idx >> 6) & 31u); }
+// dense in-range tables: 32x32 keys (both bytes in [-16,15]) = 512 words, SMALL_REP lane-selected replicas per trial
+constexpr int SMALL_REP = 4;
+constexpr uint32_t SMALL_WORDS = 512;
+__device__ __forceinline__ uint32_t small_word(uint32_t idx) { return (idx >> 1) ^ ((idx >> 5) & 15u); }
 
 // ---- shared-memory carve-up --------------------------------------------------------------------------------------
 struct Smem {
@@ -169,7 +172,7 @@ struct Smem {
     uint8_t *rows;     // 3 slots of rb bytes
     uint32_t *hist;    // [5][HIST_REP][256]
     uint32_t *table;   // 32768 words = 65536 u16 counters
-    uint32_t *small;   // [5][2048] words = five 64x64 u16 counter tables (in-range bigrams), optional
+    uint32_t *small;   // [5][SMALL_REP][512] words: 32x32 u16 counter tables (in-range bigrams), optional
     uint32_t *s_out;   // [5] outlier-window count per trial
     uint16_t *s_list;  // [5][OUT_LIST] outlier bigrams of trials with few of them
 };
@@ -188,7 +191,7 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb) {
     s.small = reinterpret_cast<uint32_t *>(p + 65536 * 2);
     return s;
 }
-constexpr uint32_t SMALL_BYTES = 5 * 4096 * 2;
+constexpr uint32_t SMALL_BYTES = 5 * SMALL_REP * SMALL_WORDS * 4;
 __host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, bool small_tab) {
     uint32_t b = SMEM_HDR + 3 * rb;
     if (sc & SC_ENTROPY) b += 5 * HIST_REP * 256 * 4;
@@ -376,14 +379,14 @@ __device__ __forceinline__ void bigram_row(const uint8_t *cur, const uint8_t *up
 
 // ---- Bigrams/BigEnt, all five trials at once (rows <= 8192 bytes) ---------------------------------------------------
 // Filtered rows of natural images are sharply peaked around 0, which makes returning atomics on one shared table
-// serialise (ncu: ~11 wavefronts per ATOMS).  Here a window whose two stream bytes both lie in [-32, 31] (as i8) is
-// counted in a dense 64x64 u16 table private to its trial with a *non-returning* add (same-address lanes combine), and
-// all five trials run in one phase; a sweep over the 5 x 4096 counters then yields distinct count and entropy with
-// no ownership bookkeeping.  The remaining (outlier) windows take the big-table / owner path, trial by trial, and
+// serialise (ncu: 10-32 wavefronts per ATOMS; same-address lanes serialise with or without a return value).  Here a
+// window whose two stream bytes both lie in [-16, 15] (as i8) is counted in a dense, bank-swizzled 32x32 u16 table
+// private to its trial and to the lane's replica (lane & 3), all five trials in one phase; a sweep over the
+// 5 x 4 x 1024 counters then yields distinct count and entropy with no ownership bookkeeping.  The remaining (outlier) windows take the big-table / owner path, trial by trial, and
 // only for trials that have any.  Exact for any data: every window is counted in exactly one of the two tables, and
 // the two key sets are disjoint.
-__device__ __forceinline__ uint32_t range_code4(uint32_t r) { // per byte: (b + 32) mod 256 (no carries across bytes)
-    return ((r & 0x7F7F7F7Fu) + 0x20202020u) ^ (r & 0x80808080u);
+__device__ __forceinline__ uint32_t range_code4(uint32_t r) { // per byte: (b + 16) mod 256 (no carries across bytes)
+    return ((r & 0x7F7F7F7Fu) + 0x10101010u) ^ (r & 0x80808080u);
 }
 template <int D, int NT, int WPT>
 __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
@@ -421,14 +424,14 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
 #pragma unroll
         for (int f = 0; f < 5; f++) {
             const uint32_t t = range_code4(r[i][f]);
-            uint32_t tp = (pv[i][f] + 32u) & 255u; // code/flags of the byte before the word
-            uint32_t *tab = sm.small + f * 2048;
+            uint32_t tp = (pv[i][f] + 16u) & 255u; // code/flags of the byte before the word
+            uint32_t *tab = sm.small + (f * SMALL_REP + (threadIdx.x & (SMALL_REP - 1))) * SMALL_WORDS;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const uint32_t tj = (t >> (8 * j)) & 255u;
                 if (j < valid) {
-                    if (((tp | tj) & 0xC0u) == 0) {
-                        const uint32_t idx = (tp << 6) | tj;
+                    if (((tp | tj) & 0xE0u) == 0) {
+                        const uint32_t idx = (tp << 5) | tj;
                         atomicAdd(&tab[small_word(idx)], (idx & 1u) ? 0x10000u : 1u);
                     } else {
                         om[f] |= 1u << (4 * i + j);
@@ -437,7 +440,7 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
                         if (*(volatile uint32_t *)&sm.s_out[f] <= (uint32_t)OUT_LIST) {
                             const uint32_t slot = atomicAdd(&sm.s_out[f], 1u);
                             if (slot < (uint32_t)OUT_LIST)
-                                sm.s_list[f * OUT_LIST + slot] = (uint16_t)((((tp + 224u) & 255u) << 8) | ((tj + 224u) & 255u));
+                                sm.s_list[f * OUT_LIST + slot] = (uint16_t)((((tp + 240u) & 255u) << 8) | ((tj + 240u) & 255u));
                         }
                     }
                 }
@@ -471,24 +474,25 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             }
         }
     }
-    // sweep the five dense tables
+    // sweep the five dense tables (sum of the replicas; clears what it finds)
     {
-        uint32_t dis[5] = {0, 0, 0, 0, 0}, ent[5] = {0, 0, 0, 0, 0};
+        for (uint32_t q = threadIdx.x; q < 5 * SMALL_WORDS; q += NT) {
+            const uint32_t f = q / SMALL_WORDS, w = q % SMALL_WORDS;
+            uint32_t *t = sm.small + f * SMALL_REP * SMALL_WORDS + w;
+            uint32_t c0 = 0, c1 = 0;
 #pragma unroll
-        for (int f = 0; f < 5; f++) {
-            for (uint32_t w = threadIdx.x; w < 2048; w += NT) {
-                const uint32_t v = sm.small[f * 2048 + w];
+            for (int rp = 0; rp < SMALL_REP; rp++) {
+                const uint32_t v = t[rp * SMALL_WORDS];
                 if (v) {
-                    sm.small[f * 2048 + w] = 0;
-                    const uint32_t c0 = v & 0xFFFFu, c1 = v >> 16;
-                    if (c0) { dis[f]++; ent[f] += ilog2i(c0); }
-                    if (c1) { dis[f]++; ent[f] += ilog2i(c1); }
+                    t[rp * SMALL_WORDS] = 0;
+                    c0 += v & 0xFFFFu;
+                    c1 += v >> 16;
                 }
             }
-        }
-#pragma unroll
-        for (int f = 0; f < 5; f++) {
-            const uint32_t d = warp_sum(dis[f]), e = warp_sum(ent[f]);
+            uint32_t d = (c0 != 0) + (c1 != 0), e = (c0 ? ilog2i(c0) : 0u) + (c1 ? ilog2i(c1) : 0u);
+            // all 32 lanes of a warp sweep the same trial (SMALL_WORDS is a multiple of 32)
+            d = warp_sum(d);
+            e = warp_sum(e);
             if ((threadIdx.x & 31) == 0 && d) {
                 atomicAdd(&sm.s_bgc[f], d);
                 atomicAdd(&sm.s_bge[f], e);
