@@ -30,6 +30,7 @@ constexpr int SC_MINSUM = 1, SC_ENTROPY = 2, SC_BIGRAM = 4;
 constexpr int HIST_REP = 4;      // copies of each Entropy histogram (lane & 3) to thin same-address atomics
 constexpr uint32_t PAD = 32;     // zero bytes in front of every staged row (left/upleft of the first pixel)
 constexpr uint32_t SMEM_HDR = 1536;
+constexpr uint32_t SCORE_WORDS = 40;   // s_min/s_ent/s_bgc/s_bge/s_out, 8 words each; three sets rotate row by row
 constexpr int OUT_LIST = 64;         // outlier bigrams per trial that are resolved by one warp instead of the big table
 constexpr uint32_t SMEM_LIMIT = 232448; // 227 KB
 
@@ -42,6 +43,7 @@ struct FastParams {
     uint32_t items_per_image;
     uint32_t rb;    // bytes of one ring slot
     uint32_t shift; // 8 * (bpp % 4): funnel-shift amount that turns a row word into its "left" word
+    uint32_t nslot;     // ring slots (4 when shared memory allows: removes the end-of-row barrier; else 3)
     uint32_t small_tab; // bigram scorer: five dense 64x64 in-range tables are carved (rows <= 8192 bytes)
 };
 
@@ -165,26 +167,27 @@ __device__ __forceinline__ uint32_t small_word(uint32_t idx) { return (idx >> 1)
 // ---- shared-memory carve-up --------------------------------------------------------------------------------------
 struct Smem {
     uint64_t *bar;     // 3 mbarriers
-    uint32_t *s_min;   // [5] MinSum sad accumulators
-    uint32_t *s_ent;   // [5]
-    uint32_t *s_bgc;   // [5] distinct bigrams
-    uint32_t *s_bge;   // [5] bigram entropy
+    uint32_t *sc;      // score set of the current row: s_min[8] s_ent[8] s_bgc[8] s_bge[8] s_out[8]
+    __device__ __forceinline__ uint32_t *s_min_() const { return sc; }      // [5] MinSum sad accumulators
+    __device__ __forceinline__ uint32_t *s_ent_() const { return sc + 8; }  // [5]
+    __device__ __forceinline__ uint32_t *s_bgc_() const { return sc + 16; } // [5] distinct bigrams
+    __device__ __forceinline__ uint32_t *s_bge_() const { return sc + 24; } // [5] bigram entropy
+    __device__ __forceinline__ uint32_t *s_out_() const { return sc + 32; } // [5] outlier windows per trial
     uint8_t *rows;     // 3 slots of rb bytes
     uint32_t *hist;    // [5][HIST_REP][256]
     uint32_t *table;   // 32768 words = 65536 u16 counters
     uint32_t *small;   // [5][SMALL_REP][512] words: 32x32 u16 counter tables (in-range bigrams), optional
-    uint32_t *s_out;   // [5] outlier-window count per trial
     uint16_t *s_list;  // [5][OUT_LIST] outlier bigrams of trials with few of them
 };
 template <int SC>
-__device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb) {
+__device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot) {
     Smem s;
     s.bar = reinterpret_cast<uint64_t *>(base);
     uint32_t *u = reinterpret_cast<uint32_t *>(base + 64);
-    s.s_min = u; s.s_ent = u + 8; s.s_bgc = u + 16; s.s_bge = u + 24; s.s_out = u + 32;
+    s.sc = u; // set 0; sets 1 and 2 follow at SCORE_WORDS strides
     s.s_list = reinterpret_cast<uint16_t *>(base + 768);
     s.rows = base + SMEM_HDR;
-    uint8_t *p = s.rows + 3 * (size_t)rb;
+    uint8_t *p = s.rows + nslot * (size_t)rb;
     s.hist = reinterpret_cast<uint32_t *>(p);
     if (SC & SC_ENTROPY) p += 5 * HIST_REP * 256 * 4;
     s.table = reinterpret_cast<uint32_t *>(p);
@@ -192,8 +195,8 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb) {
     return s;
 }
 constexpr uint32_t SMALL_BYTES = 5 * SMALL_REP * SMALL_WORDS * 4;
-__host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, bool small_tab) {
-    uint32_t b = SMEM_HDR + 3 * rb;
+__host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, bool small_tab, uint32_t nslot = 3) {
+    uint32_t b = SMEM_HDR + nslot * rb;
     if (sc & SC_ENTROPY) b += 5 * HIST_REP * 256 * 4;
     if (sc & SC_BIGRAM) b += 65536 * 2 + (small_tab ? SMALL_BYTES : 0);
     return b;
@@ -437,8 +440,8 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
                         om[f] |= 1u << (4 * i + j);
                         // claim a slot in the trial's short outlier list (the count keeps growing past the list size)
                         // (once the count has passed the list size nobody needs to add any more: "many" is enough)
-                        if (*(volatile uint32_t *)&sm.s_out[f] <= (uint32_t)OUT_LIST) {
-                            const uint32_t slot = atomicAdd(&sm.s_out[f], 1u);
+                        if (*(volatile uint32_t *)&sm.s_out_()[f] <= (uint32_t)OUT_LIST) {
+                            const uint32_t slot = atomicAdd(&sm.s_out_()[f], 1u);
                             if (slot < (uint32_t)OUT_LIST)
                                 sm.s_list[f * OUT_LIST + slot] = (uint16_t)((((tp + 240u) & 255u) << 8) | ((tj + 240u) & 255u));
                         }
@@ -452,7 +455,7 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
     // trials with only a few outliers: warp f dedupes the list of trial f by brute force (no table, no barrier)
     if ((threadIdx.x >> 5) < 5) {
         const int f = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const uint32_t n = sm.s_out[f];
+        const uint32_t n = sm.s_out_()[f];
         if (n > 0 && n <= (uint32_t)OUT_LIST) {
             uint32_t dis = 0, ent = 0;
             for (uint32_t e = lane; e < n; e += 32) {
@@ -469,8 +472,8 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             dis = warp_sum(dis);
             ent = warp_sum(ent);
             if (lane == 0) {
-                atomicAdd(&sm.s_bgc[f], dis);
-                atomicAdd(&sm.s_bge[f], ent);
+                atomicAdd(&sm.s_bgc_()[f], dis);
+                atomicAdd(&sm.s_bge_()[f], ent);
             }
         }
     }
@@ -494,8 +497,8 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             d = warp_sum(d);
             e = warp_sum(e);
             if ((threadIdx.x & 31) == 0 && d) {
-                atomicAdd(&sm.s_bgc[f], d);
-                atomicAdd(&sm.s_bge[f], e);
+                atomicAdd(&sm.s_bgc_()[f], d);
+                atomicAdd(&sm.s_bge_()[f], e);
             }
         }
     }
@@ -503,7 +506,7 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
     uint16_t *t16 = reinterpret_cast<uint16_t *>(sm.table);
 #pragma unroll
     for (int f = 0; f < 5; f++) {
-        if (sm.s_out[f] <= (uint32_t)OUT_LIST) continue; // uniform: final before the barrier above; few -> done by a warp
+        if (sm.s_out_()[f] <= (uint32_t)OUT_LIST) continue; // uniform: final before the barrier above; few -> done by a warp
         uint32_t own = 0;
 #pragma unroll
         for (int i = 0; i < WPT; i++) {
@@ -542,8 +545,8 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
         distinct = warp_sum(distinct);
         ent = warp_sum(ent);
         if ((threadIdx.x & 31) == 0 && distinct) {
-            atomicAdd(&sm.s_bgc[f], distinct);
-            atomicAdd(&sm.s_bge[f], ent);
+            atomicAdd(&sm.s_bgc_()[f], distinct);
+            atomicAdd(&sm.s_bge_()[f], ent);
         }
         __syncthreads();
     }
@@ -611,17 +614,18 @@ template <int D, int SC>
 __global__ void __launch_bounds__(threads_for(SC), 1) k_fast(const __grid_constant__ FastParams P) {
     constexpr int NT = threads_for(SC);
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const Smem sm = carve<SC>(smem_raw, P.rb);
+    const uint32_t NS = P.nslot;
+    const Smem sm = carve<SC>(smem_raw, P.rb, NS);
     const int tid = threadIdx.x;
     const int bpp = (int)P.g.bpp;
     const uint32_t shift = P.shift;
 
     if (tid == 0) {
-        mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_init(&sm.bar[2], 1);
+        for (uint32_t i = 0; i < NS; i++) mbar_init(&sm.bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 40) sm.s_min[tid] = 0;
-    for (uint32_t i = tid; i < 3 * PAD / 4; i += NT) // zero the left pad of each slot (never written again)
+    if (tid < 3 * (int)SCORE_WORDS) sm.sc[tid] = 0; // the three rotating score sets
+    for (uint32_t i = tid; i < NS * PAD / 4; i += NT) // zero the left pad of each slot (never written again)
         reinterpret_cast<uint32_t *>(sm.rows + (i / (PAD / 4)) * (size_t)P.rb)[i % (PAD / 4)] = 0;
     if (SC & SC_ENTROPY)
         for (uint32_t i = tid; i < 5 * HIST_REP * 256; i += NT) sm.hist[i] = 0;
@@ -632,10 +636,14 @@ __global__ void __launch_bounds__(threads_for(SC), 1) k_fast(const __grid_consta
     }
     __syncthreads();
 
-    uint32_t parity = 0; // bit s = phase to wait for on slot s
+    uint32_t parity = 0;  // bit s = phase to wait for on slot s
+    uint32_t row_ctr = 0; // rows scored by this CTA so far: selects the score set
     const uint64_t total_items = P.n_images * (uint64_t)P.items_per_image;
     bool any_heur = false;
     for (int j = 0; j < P.set.k; j++) any_heur |= (P.set.s[j].kind != OXI_BASIC && P.set.s[j].kind != OXI_PREDEFINED);
+    // With a 4-slot ring a slot is refilled two iterations after its last reader, and every scored row contains at
+    // least one CTA-wide barrier, so the end-of-row barrier is only needed for the 3-slot ring / unscored rows.
+    const bool row_end_barrier = NS < 4 || SC == 0 || !any_heur;
 
     for (uint64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
         const uint64_t img = item / P.items_per_image;
@@ -678,7 +686,7 @@ __global__ void __launch_bounds__(threads_for(SC), 1) k_fast(const __grid_consta
         __syncthreads();
 
         for (uint32_t k = k0; k < k1; k++) {
-            const uint32_t j = k - k0 + 1, sc_ = j % 3, sp = (j + 2) % 3, sn = (j + 1) % 3;
+            const uint32_t j = k - k0 + 1, sc_ = j % NS, sp = (j + NS - 1) % NS, sn = (j + 1) % NS;
             const uint8_t *cur = sm.rows + sc_ * (size_t)P.rb + PAD;
             const uint8_t *up = sm.rows + sp * (size_t)P.rb + PAD;
             if (k + 1 < k1) { // stream the next row in behind the current one
@@ -700,8 +708,28 @@ __global__ void __launch_bounds__(threads_for(SC), 1) k_fast(const __grid_consta
             const uint32_t r = pd.row0 + k;
             const uint64_t in_off = pd.in_base + (uint64_t)k * len;
             bool heur = false;
+            // score set of this row; the set of the row after next is cleared here, before this row's barriers:
+            // its last readers (decisions two rows ago) are behind the previous row's barriers
+            Smem sr = sm;
+            sr.sc = sm.sc + (row_ctr % 3u) * SCORE_WORDS;
             if (SC != 0 && any_heur) {
-                // all-zero rows short-circuit to None (png/mod.rs:398-404)
+                if (tid < (int)SCORE_WORDS) sm.sc[((row_ctr + 1u) % 3u) * SCORE_WORDS + tid] = 0;
+                if (SC & SC_MINSUM) minsum_pass<D, NT>(cur, up, len, shift, sr.s_min_());
+                if (SC & SC_ENTROPY) {
+                    entropy_pass<D, NT>(cur, up, len, shift, sm.hist);
+                    __syncthreads();
+                    entropy_score<NT>(sm.hist, sr.s_ent_());
+                }
+                if (SC & SC_BIGRAM) {
+                    const uint32_t wpt = (((len + 3) >> 2) + NT - 1) / NT; // row words per thread
+                    if (P.small_tab && wpt <= 1) bigram_row_small<D, NT, 1>(cur, up, len, shift, bpp, sr);
+                    else if (P.small_tab && wpt <= 2) bigram_row_small<D, NT, 2>(cur, up, len, shift, bpp, sr);
+                    else if (wpt <= 1) bigram_row<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
+                    else if (wpt <= 2) bigram_row<D, NT, 2>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
+                    else if (wpt <= 4) bigram_row<D, NT, 4>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
+                    else bigram_row<D, NT, 8>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
+                }
+                // all-zero rows short-circuit to None (png/mod.rs:398-404); decided at the scorers' last barrier
                 uint32_t nz = 0;
                 const uint4 *c4 = reinterpret_cast<const uint4 *>(cur);
                 const uint32_t nchunks = (len + 15) >> 4;
@@ -714,26 +742,8 @@ __global__ void __launch_bounds__(threads_for(SC), 1) k_fast(const __grid_consta
                     }
                     nz |= v.x | v.y | v.z | v.w;
                 }
-                if (tid < 40) sm.s_min[tid] = 0; // clears s_min, s_ent, s_bgc, s_bge, s_out
                 heur = __syncthreads_or(nz != 0) != 0;
-                if (heur) {
-                    if (SC & SC_MINSUM) minsum_pass<D, NT>(cur, up, len, shift, sm.s_min);
-                    if (SC & SC_ENTROPY) {
-                        entropy_pass<D, NT>(cur, up, len, shift, sm.hist);
-                        __syncthreads();
-                        entropy_score<NT>(sm.hist, sm.s_ent);
-                    }
-                    if (SC & SC_BIGRAM) {
-                        const uint32_t wpt = (((len + 3) >> 2) + NT - 1) / NT; // row words per thread
-                        if (P.small_tab && wpt <= 1) bigram_row_small<D, NT, 1>(cur, up, len, shift, bpp, sm);
-                        else if (P.small_tab && wpt <= 2) bigram_row_small<D, NT, 2>(cur, up, len, shift, bpp, sm);
-                        else if (wpt <= 1) bigram_row<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
-                        else if (wpt <= 2) bigram_row<D, NT, 2>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
-                        else if (wpt <= 4) bigram_row<D, NT, 4>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
-                        else bigram_row<D, NT, 8>(cur, up, len, shift, bpp, sm.table, sm.s_bgc, sm.s_bge);
-                    }
-                    __syncthreads();
-                }
+                row_ctr++;
             }
 
             for (int j2 = 0; j2 < P.set.k; j2++) {
@@ -749,18 +759,18 @@ __global__ void __launch_bounds__(threads_for(SC), 1) k_fast(const __grid_consta
                         const uint32_t nbytes = 16 * ((len + 15) >> 4);
 #pragma unroll
                         for (int q = 0; q < 5; q++) {
-                            const uint32_t s = 128u * nbytes - sm.s_min[q] + (uint32_t)q;
+                            const uint32_t s = 128u * nbytes - sr.s_min_()[q] + (uint32_t)q;
                             if (s < best || q == 0) { best = s; f = q; }
                         }
                     } else if (st.kind == OXI_BIGRAMS) { // fewer distinct bigrams, strict '<' (strategies.rs:182-189)
                         uint32_t best = 0;
 #pragma unroll
                         for (int q = 0; q < 5; q++) {
-                            const uint32_t s = sm.s_bgc[q];
+                            const uint32_t s = sr.s_bgc_()[q];
                             if (q == 0 || s < best) { best = s; f = q; }
                         }
                     } else { // Entropy / BigEnt: larger is better, strict '>' on i32 (strategies.rs:143,221)
-                        const uint32_t *sc = st.kind == OXI_ENTROPY ? sm.s_ent : sm.s_bge;
+                        const uint32_t *sc = st.kind == OXI_ENTROPY ? sr.s_ent_() : sr.s_bge_();
                         int32_t best = 0;
 #pragma unroll
                         for (int q = 0; q < 5; q++) {
@@ -772,8 +782,9 @@ __global__ void __launch_bounds__(threads_for(SC), 1) k_fast(const __grid_consta
                 write_row<NT>(f, cur, up, len, bpp, st.out + img * P.g.out_len + in_off + r);
                 if (tid == 0) st.filters_used[img * P.g.total_rows + r] = (uint8_t)f;
             }
-            __syncthreads(); // slot `sp` may be refilled by the next iteration's prefetch
+            if (row_end_barrier) __syncthreads(); // slot `sp` may be refilled by the next iteration's prefetch
         }
+        if (!row_end_barrier) __syncthreads(); // the next band's prologue rewrites slots 0 and 1
     }
 }
 
@@ -837,7 +848,9 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
     P.rb = slot_bytes(g);
     P.shift = 8 * (g.bpp % 4);
     P.small_tab = (sc & SC_BIGRAM) && g.max_len <= 8192 && smem_bytes_for(sc, P.rb, true) <= SMEM_LIMIT;
-    const uint32_t smem = smem_bytes_for(sc, P.rb, P.small_tab != 0);
+    // a fourth ring slot removes the end-of-row barrier; take it when it does not cost occupancy (rows <= 16 KB)
+    P.nslot = (sc != 0 && P.rb <= 16448 && smem_bytes_for(sc, P.rb, P.small_tab != 0, 4) <= SMEM_LIMIT) ? 4 : 3;
+    const uint32_t smem = smem_bytes_for(sc, P.rb, P.small_tab != 0, P.nslot);
     KernelFn fn = pick_kernel((int)(g.bpp / 4), sc);
     cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
