@@ -96,7 +96,8 @@ def workload_config(args, images_this_step=None):
                         "(-o4 set without Brute), sharded by image",
             "images_per_gpu": args.images_per_gpu, "image": "1024x1024 RGBA8 (4 194 304 B, 1024 scanlines)",
             "strategies": ["None", "Bigrams", "BigEnt"], "optimize_alpha": False,
-            "l2": "per-GPU input 5.2 GB and output 15.7 GB >> 126 MB L2; no flush needed",
+            "l2": f"per-GPU input {args.images_per_gpu * PER_IMAGE / 1e9:.2f} GB and output "
+                  f"{3 * args.images_per_gpu * (PER_IMAGE + ROWS) / 1e9:.2f} GB per step vs 126 MB L2: no flush needed",
             "images_in_step": images_this_step}
 
 
@@ -269,7 +270,7 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("c5_bytes_per_launch_at_bench_batch")
+            traffic = json.load(open(tp)).get("c5_dram_bytes_per_image") * B  # per launch, scaled from the 64-image capture
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
