@@ -611,7 +611,7 @@ __device__ __forceinline__ void coop_load_row(uint8_t *dst, const uint8_t *src, 
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 template <int D, int SC>
-__global__ void __launch_bounds__(threads_for(SC), (SC & SC_BIGRAM) ? 1 : 2) k_fast(const __grid_constant__ FastParams P) {
+__global__ void __launch_bounds__(threads_for(SC), (SC & SC_BIGRAM) ? 1 : (SC == SC_MINSUM || SC == 0) ? 3 : 2) k_fast(const __grid_constant__ FastParams P) {
     constexpr int NT = threads_for(SC);
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t NS = P.nslot;
