@@ -384,8 +384,10 @@ __device__ __forceinline__ void bigram_row(const uint8_t *cur, const uint8_t *up
 // Filtered rows of natural images are sharply peaked around 0, which makes returning atomics on one shared table
 // serialise (ncu: 10-32 wavefronts per ATOMS; same-address lanes serialise with or without a return value).  Here a
 // window whose two stream bytes both lie in [-16, 15] (as i8) is counted in a dense, bank-swizzled 32x32 u16 table
-// private to its trial and to the lane's replica (lane & 3), all five trials in one phase; a sweep over the
-// 5 x 4 x 1024 counters then yields distinct count and entropy with no ownership bookkeeping.  The remaining (outlier) windows take the big-table / owner path, trial by trial, and
+// private to its trial and to the lane's replica (lane & 3), trials 1..4 in one phase; a sweep over the 4 x 4 x 1024
+// counters then yields distinct count and entropy with no ownership bookkeeping.  Trial 0 (None: the raw bytes) is
+// almost never near zero, so it goes straight to the 65536-entry table in the same phase (returning adds, the first
+// adder owns the bigram) and its owners read/clear the counts while the other trials are being swept.  The remaining (outlier) windows take the big-table / owner path, trial by trial, and
 // only for trials that have any.  Exact for any data: every window is counted in exactly one of the two tables, and
 // the two key sets are disjoint.
 __device__ __forceinline__ uint32_t range_code4(uint32_t r) { // per byte: (b + 16) mod 256 (no carries across bytes)
@@ -396,8 +398,9 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
                                                  const Smem &sm) {
     const uint32_t nwords = (len + 3) >> 2;
     const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur), *uw = reinterpret_cast<const uint32_t *>(up);
+    uint16_t *t16 = reinterpret_cast<uint16_t *>(sm.table);
     uint32_t r[WPT][5], pv[WPT][5];
-    uint32_t om[5] = {0, 0, 0, 0, 0}; // outlier windows of this thread, bit 4*i+j
+    uint32_t om[5] = {0, 0, 0, 0, 0}; // trial 0: windows this thread owns in the big table; 1..4: its outlier windows
 #pragma unroll
     for (int i = 0; i < WPT; i++) {
         const uint32_t k = threadIdx.x + i * NT;
@@ -424,8 +427,22 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             pv[i][f] = p;
         }
         const int valid = (int)len - 4 * kk;
+        // trial 0 (None = the raw bytes, rarely near zero): straight to the big table, this thread owns what it adds first
+        {
+            uint32_t prev = pv[i][0];
 #pragma unroll
-        for (int f = 0; f < 5; f++) {
+            for (int j = 0; j < 4; j++) {
+                const uint32_t b = (x >> (8 * j)) & 255u;
+                const uint32_t bg = (prev << 8) | b;
+                prev = b;
+                if (j < valid) {
+                    const uint32_t old = atomicAdd(&sm.table[big_word(bg)], (bg & 1u) ? 0x10000u : 1u);
+                    if (((bg & 1u) ? (old >> 16) : (old & 0xFFFFu)) == 0) om[0] |= 1u << (4 * i + j);
+                }
+            }
+        }
+#pragma unroll
+        for (int f = 1; f < 5; f++) {
             const uint32_t t = range_code4(r[i][f]);
             uint32_t tp = (pv[i][f] + 16u) & 255u; // code/flags of the byte before the word
             uint32_t *tab = sm.small + (f * SMALL_REP + (threadIdx.x & (SMALL_REP - 1))) * SMALL_WORDS;
@@ -452,8 +469,36 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
         }
     }
     __syncthreads();
+    // trial 0: owners read the final counts and clear the entries (no other trial is in the big table now)
+    {
+        uint32_t distinct = 0, ent = 0;
+        if (om[0]) {
+#pragma unroll
+            for (int i = 0; i < WPT; i++) {
+                uint32_t prev = pv[i][0];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t b = (r[i][0] >> (8 * j)) & 255u;
+                    const uint32_t bg = (prev << 8) | b;
+                    prev = b;
+                    if ((om[0] >> (4 * i + j)) & 1u) {
+                        const uint32_t cnt = t16[(big_word(bg) << 1) | (bg & 1u)];
+                        t16[(big_word(bg) << 1) | (bg & 1u)] = 0;
+                        distinct += 1;
+                        ent += ilog2i(cnt);
+                    }
+                }
+            }
+        }
+        distinct = warp_sum(distinct);
+        ent = warp_sum(ent);
+        if ((threadIdx.x & 31) == 0 && distinct) {
+            atomicAdd(&sm.s_bgc_()[0], distinct);
+            atomicAdd(&sm.s_bge_()[0], ent);
+        }
+    }
     // trials with only a few outliers: warp f dedupes the list of trial f by brute force (no table, no barrier)
-    if ((threadIdx.x >> 5) < 5) {
+    if ((threadIdx.x >> 5) >= 1 && (threadIdx.x >> 5) < 5) {
         const int f = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const uint32_t n = sm.s_out_()[f];
         if (n > 0 && n <= (uint32_t)OUT_LIST) {
@@ -477,36 +522,36 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             }
         }
     }
-    // sweep the five dense tables (sum of the replicas; clears what it finds)
-    {
-        for (uint32_t q = threadIdx.x; q < 5 * SMALL_WORDS; q += NT) {
-            const uint32_t f = q / SMALL_WORDS, w = q % SMALL_WORDS;
-            uint32_t *t = sm.small + f * SMALL_REP * SMALL_WORDS + w;
-            uint32_t c0 = 0, c1 = 0;
+    // sweep the dense tables of trials 1..4 (sum of the replicas; clears what it finds)
+    for (uint32_t q = SMALL_WORDS + threadIdx.x; q < 5 * SMALL_WORDS; q += NT) {
+        const uint32_t f = q / SMALL_WORDS, w = q % SMALL_WORDS;
+        uint32_t *t = sm.small + f * SMALL_REP * SMALL_WORDS + w;
+        uint32_t c0 = 0, c1 = 0;
 #pragma unroll
-            for (int rp = 0; rp < SMALL_REP; rp++) {
-                const uint32_t v = t[rp * SMALL_WORDS];
-                if (v) {
-                    t[rp * SMALL_WORDS] = 0;
-                    c0 += v & 0xFFFFu;
-                    c1 += v >> 16;
-                }
-            }
-            uint32_t d = (c0 != 0) + (c1 != 0), e = (c0 ? ilog2i(c0) : 0u) + (c1 ? ilog2i(c1) : 0u);
-            // all 32 lanes of a warp sweep the same trial (SMALL_WORDS is a multiple of 32)
-            d = warp_sum(d);
-            e = warp_sum(e);
-            if ((threadIdx.x & 31) == 0 && d) {
-                atomicAdd(&sm.s_bgc_()[f], d);
-                atomicAdd(&sm.s_bge_()[f], e);
+        for (int rp = 0; rp < SMALL_REP; rp++) {
+            const uint32_t v = t[rp * SMALL_WORDS];
+            if (v) {
+                t[rp * SMALL_WORDS] = 0;
+                c0 += v & 0xFFFFu;
+                c1 += v >> 16;
             }
         }
+        uint32_t d = (c0 != 0) + (c1 != 0), e = (c0 ? ilog2i(c0) : 0u) + (c1 ? ilog2i(c1) : 0u);
+        // all 32 lanes of a warp sweep the same trial (SMALL_WORDS is a multiple of 32)
+        d = warp_sum(d);
+        e = warp_sum(e);
+        if ((threadIdx.x & 31) == 0 && d) {
+            atomicAdd(&sm.s_bgc_()[f], d);
+            atomicAdd(&sm.s_bge_()[f], e);
+        }
     }
-    // outlier windows: big table, owner pass, one trial at a time
-    uint16_t *t16 = reinterpret_cast<uint16_t *>(sm.table);
+    // trials 1..4 with many outliers: big table + owner pass, one trial at a time (after trial 0 has cleaned up)
+    const bool any_heavy = sm.s_out_()[1] > (uint32_t)OUT_LIST || sm.s_out_()[2] > (uint32_t)OUT_LIST ||
+                           sm.s_out_()[3] > (uint32_t)OUT_LIST || sm.s_out_()[4] > (uint32_t)OUT_LIST; // uniform
+    if (any_heavy) __syncthreads();
 #pragma unroll
-    for (int f = 0; f < 5; f++) {
-        if (sm.s_out_()[f] <= (uint32_t)OUT_LIST) continue; // uniform: final before the barrier above; few -> done by a warp
+    for (int f = 1; f < 5; f++) {
+        if (sm.s_out_()[f] <= (uint32_t)OUT_LIST) continue; // uniform: final before the first barrier above
         uint32_t own = 0;
 #pragma unroll
         for (int i = 0; i < WPT; i++) {
