@@ -33,6 +33,7 @@ extern "C" {
 #define OXI_E_CUDA (-2)
 #define OXI_E_NOMEM (-3)
 #define OXI_E_UNSUPPORTED (-4)
+#define OXI_E_DATA (-5) /* PngError::InvalidData */
 
 /* IhdrData, src/headers.rs:15-26; colour-type codes src/colors.rs:48-56; BitDepth src/colors.rs:96-107 */
 typedef struct oxi_ihdr {
@@ -154,6 +155,17 @@ int oxi_cooccurrence_build(const oxi_ihdr *, uint32_t num_colors, const uint8_t 
 /* apply_palette_reorder, palette.rs:165-194; remapping[i] = old index placed at new index i */
 int oxi_apply_palette_reorder(const oxi_ihdr *, const oxi_color_aux *, const uint32_t *remapping, const uint8_t *data,
                               size_t data_len, uint8_t *out, oxi_color_aux *out_aux);
+
+/* ---- "next" rows of the scope table: the steps either side of the hot path ---------------------- */
+/* PngImage::unfilter_image, src/png/mod.rs:335-351 (+ RowFilter::unfilter_line, src/filters/mod.rs:188-239): the
+ * inflated IDAT stream (one filter-type byte in front of every scanline) -> PngImage.data. out: len bytes suffice.
+ * Returns OXI_E_DATA for a filter type > 4 (the reference's PngError::InvalidData). */
+int oxi_unfilter_image(const oxi_ihdr *, const uint8_t *filtered, size_t len, uint8_t *out, size_t *out_len);
+/* interlace_image, src/interlace.rs:6-60: progressive layout -> Adam7 layout (ihdr describes the image; its
+ * `interlaced` flag is ignored). out: oxi_raw_data_size(interlaced ihdr) - rows bytes at most (<= data_len + 7*height). */
+int oxi_interlace_image(const oxi_ihdr *, const uint8_t *data, size_t data_len, uint8_t *out, size_t *out_len);
+/* deinterlace_image, src/interlace.rs:62-150: Adam7 layout -> progressive layout. out: ceil(width*bpp/8)*height */
+int oxi_deinterlace_image(const oxi_ihdr *, const uint8_t *data, size_t data_len, uint8_t *out, size_t *out_len);
 
 #ifdef __cplusplus
 }

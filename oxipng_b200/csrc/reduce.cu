@@ -488,6 +488,153 @@ __global__ void k_symmetrise(uint32_t *m, uint32_t n) {
     m[j * n + i] = s;
 }
 
+
+// ---- interlace.rs: Adam7 as a pure gather ----------------------------------------------------------
+struct Adam7 {
+    uint32_t width, height, bits; // bits per pixel
+    uint32_t pw[7], ph[7];        // pixels per row / rows of each pass (0 = empty pass)
+    uint32_t stride[7];           // bytes per pass row
+    uint64_t base[8];             // byte offset of each pass in the interlaced layout; base[7] = total
+    uint32_t full_stride;         // bytes per row of the progressive layout
+};
+__constant__ uint8_t kA7x0[7] = {0, 4, 0, 2, 0, 1, 0}, kA7y0[7] = {0, 0, 4, 0, 2, 0, 1};
+__constant__ uint8_t kA7dx[7] = {8, 8, 4, 4, 2, 2, 1}, kA7dy[7] = {8, 8, 8, 4, 4, 2, 2};
+
+__device__ __forceinline__ uint32_t get_bits(const uint8_t *row, uint32_t bit, uint32_t nbits) { // nbits in {1,2,4}
+    return (row[bit >> 3] >> (8 - nbits - (bit & 7u))) & ((1u << nbits) - 1u);
+}
+
+// interlace_image (interlace.rs:6-60): one thread per byte of the interlaced layout
+__global__ void __launch_bounds__(RT) k_interlace(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, Adam7 a) {
+    const uint64_t total = a.base[7], step = (uint64_t)gridDim.x * RT;
+    for (uint64_t o = (uint64_t)blockIdx.x * RT + threadIdx.x; o < total; o += step) {
+        int p = 0;
+#pragma unroll
+        for (int i = 1; i < 7; i++)
+            if (o >= a.base[i]) p = i;
+        const uint64_t local = o - a.base[p];
+        const uint32_t r = (uint32_t)(local / a.stride[p]), ob = (uint32_t)(local % a.stride[p]);
+        const uint8_t *src = in + (uint64_t)(kA7y0[p] + r * kA7dy[p]) * a.full_stride;
+        uint32_t v = 0;
+        if (a.bits >= 8) {
+            const uint32_t B = a.bits >> 3, c = ob / B, b = ob % B;
+            v = src[(uint64_t)(kA7x0[p] + c * kA7dx[p]) * B + b];
+        } else {
+            const uint32_t ppb = 8 / a.bits;
+            for (uint32_t q = 0; q < ppb; q++) {
+                const uint32_t c = ob * ppb + q;
+                if (c < a.pw[p]) v |= get_bits(src, (kA7x0[p] + c * kA7dx[p]) * a.bits, a.bits) << (8 - a.bits * (q + 1));
+            }
+        }
+        out[o] = (uint8_t)v;
+    }
+}
+
+// deinterlace_image (interlace.rs:62-150): one thread per byte of the progressive layout
+__global__ void __launch_bounds__(RT) k_deinterlace(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, Adam7 a) {
+    // pass of pixel (x & 7, y & 7)
+    const uint8_t pass_of[64] = {0, 5, 3, 5, 1, 5, 3, 5, 6, 6, 6, 6, 6, 6, 6, 6, 4, 5, 4, 5, 4, 5, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6,
+                                 2, 5, 3, 5, 2, 5, 3, 5, 6, 6, 6, 6, 6, 6, 6, 6, 4, 5, 4, 5, 4, 5, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6};
+    const uint64_t total = (uint64_t)a.full_stride * a.height, step = (uint64_t)gridDim.x * RT;
+    for (uint64_t o = (uint64_t)blockIdx.x * RT + threadIdx.x; o < total; o += step) {
+        const uint32_t y = (uint32_t)(o / a.full_stride), ob = (uint32_t)(o % a.full_stride);
+        uint32_t v = 0;
+        if (a.bits >= 8) {
+            const uint32_t B = a.bits >> 3, x = ob / B, b = ob % B;
+            const int p = pass_of[(y & 7u) * 8 + (x & 7u)];
+            const uint32_t c = (x - kA7x0[p]) / kA7dx[p], r = (y - kA7y0[p]) / kA7dy[p];
+            v = in[a.base[p] + (uint64_t)r * a.stride[p] + (uint64_t)c * B + b];
+        } else {
+            const uint32_t ppb = 8 / a.bits;
+            for (uint32_t q = 0; q < ppb; q++) {
+                const uint32_t x = ob * ppb + q;
+                if (x >= a.width) break;
+                const int p = pass_of[(y & 7u) * 8 + (x & 7u)];
+                const uint32_t c = (x - kA7x0[p]) / kA7dx[p], r = (y - kA7y0[p]) / kA7dy[p];
+                v |= get_bits(in + a.base[p] + (uint64_t)r * a.stride[p], c * a.bits, a.bits) << (8 - a.bits * (q + 1));
+            }
+        }
+        out[o] = (uint8_t)v;
+    }
+}
+
+
+// ---- unfilter_image (png/mod.rs:335-351, filters/mod.rs:188-239), SURVEY 8f row 1 ----------------------------------
+// Reconstruction is a recurrence along the row (Sub/Average/Paeth use the rebuilt left pixel) and across rows
+// (Up/Average/Paeth use the rebuilt previous row).  One warp takes one (image, pass) and walks it in tiles of 32
+// rows in skewed lockstep: at step s lane l rebuilds pixel s-l of row k0+l, so the pixel above it (lane l-1) was
+// finished in the step before and arrives by shuffle, "upleft" is the value shuffled in one step earlier and "left"
+// never leaves the lane's registers.  Parallelism: 32 rows per warp, warps over images and Adam7 passes.
+__device__ __forceinline__ uint32_t paeth4_u(uint32_t a, uint32_t b, uint32_t c) { // byte-wise paeth_predictor
+    uint32_t r = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) r |= paeth((a >> (8 * j)) & 255u, (b >> (8 * j)) & 255u, (c >> (8 * j)) & 255u) << (8 * j);
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_bytes(const uint8_t *p, int n) { // n <= 4 bytes, little endian
+    uint32_t v = 0;
+    for (int j = 0; j < n; j++) v |= (uint32_t)p[j] << (8 * j);
+    return v;
+}
+__device__ __forceinline__ void st_bytes(uint8_t *p, uint32_t v, int n) {
+    for (int j = 0; j < n; j++) p[j] = (uint8_t)(v >> (8 * j));
+}
+__global__ void __launch_bounds__(128) k_unfilter(Geom g, const uint8_t *__restrict__ in, uint8_t *out, uint64_t n_images,
+                                                   uint64_t in_stride, ScanState *st) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t item = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= n_images * g.n_pass) return;
+    const uint64_t img = item / g.n_pass;
+    const PassDesc pd = g.pass[item % g.n_pass];
+    const int bpp = (int)g.bpp, n0 = bpp < 4 ? bpp : 4, n1 = bpp - n0; // pixel = word0 (n0 bytes) + word1 (n1 bytes)
+    const uint32_t len = pd.len, npix = len / bpp;
+    // filtered stream: row r of the image starts at in_base + r (one filter byte per earlier row), then 1 + len bytes
+    const uint8_t *src = in + img * in_stride + pd.in_base + pd.row0;
+    uint8_t *dst = out + img * g.data_len + pd.in_base;
+    for (uint32_t k0 = 0; k0 < pd.nrows; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const bool valid = k < pd.nrows;
+        const uint8_t *frow = src + (uint64_t)k * (len + 1);
+        uint8_t *orow = dst + (uint64_t)k * len;
+        uint32_t f = valid ? frow[0] : 0;
+        if (f > 4) { st->fail = 1; f = 0; } // RowFilter::try_from fails -> PngError::InvalidData
+        const uint8_t *uprow = (lane == 0 && k > 0) ? orow - len : nullptr; // rebuilt by the previous tile (or zeros)
+        uint32_t l0 = 0, l1 = 0, u0 = 0, u1 = 0; // left pixel (own last result), up pixel of the previous step
+        const uint32_t steps = npix + 31;
+        for (uint32_t s = 0; s < steps; s++) {
+            // pixel above: the lane above finished it in the previous step
+            uint32_t a0 = __shfl_up_sync(0xffffffffu, l0, 1), a1 = __shfl_up_sync(0xffffffffu, l1, 1);
+            const int x = (int)s - (int)lane;
+            const bool act = valid && x >= 0 && x < (int)npix;
+            if (lane == 0) {
+                a0 = a1 = 0;
+                if (uprow && act) {
+                    a0 = ld_bytes(uprow + (size_t)x * bpp, n0);
+                    if (n1) a1 = ld_bytes(uprow + (size_t)x * bpp + 4, n1);
+                }
+            }
+            if (act) {
+                const uint32_t d0 = ld_bytes(frow + 1 + (size_t)x * bpp, n0);
+                const uint32_t d1 = n1 ? ld_bytes(frow + 1 + (size_t)x * bpp + 4, n1) : 0u;
+                uint32_t p0, p1;
+                switch (f) {
+                case 0: p0 = p1 = 0; break;
+                case 1: p0 = l0; p1 = l1; break;
+                case 2: p0 = a0; p1 = a1; break;
+                case 3: p0 = __vhaddu4(l0, a0); p1 = __vhaddu4(l1, a1); break;
+                default: p0 = paeth4_u(l0, a0, u0); p1 = n1 ? paeth4_u(l1, a1, u1) : 0u; break;
+                }
+                const uint32_t r0 = __vadd4(d0, p0), r1 = __vadd4(d1, p1);
+                st_bytes(orow + (size_t)x * bpp, r0, n0);
+                if (n1) st_bytes(orow + (size_t)x * bpp + 4, r1, n1);
+                l0 = r0; l1 = r1;
+            }
+            u0 = a0; u1 = a1; // becomes "upleft" of the next step
+        }
+        __syncwarp(); // the next tile's first row reads the last row of this one
+    }
+}
+
 // ---- host-side call scaffolding -------------------------------------------------------------------------------------------
 
 struct Call {
@@ -977,6 +1124,87 @@ int oxi_apply_palette_reorder(const oxi_ihdr *h, const oxi_color_aux *aux, const
     if (int rc = run_lut(call, len, byte_map)) return rc;
     if (int rc = call.download(out, len)) return rc;
     if (oaux) *oaux = na;
+    return OXI_OK;
+}
+
+
+static bool make_adam7(const oxi_ihdr *h, Adam7 *a) {
+    static const uint32_t x0[7] = {0, 4, 0, 2, 0, 1, 0}, y0[7] = {0, 0, 4, 0, 2, 0, 1};
+    static const uint32_t dx[7] = {8, 8, 4, 4, 2, 2, 1}, dy[7] = {8, 8, 8, 4, 4, 2, 2};
+    memset(a, 0, sizeof *a);
+    a->width = h->width; a->height = h->height;
+    a->bits = (uint32_t)(h->bit_depth * channels(h->color_type));
+    a->full_stride = (uint32_t)(((uint64_t)h->width * a->bits + 7) / 8);
+    uint64_t off = 0;
+    for (int p = 0; p < 7; p++) {
+        a->base[p] = off;
+        if (h->width > x0[p] && h->height > y0[p]) {
+            a->pw[p] = (h->width - x0[p] + dx[p] - 1) / dx[p];
+            a->ph[p] = (h->height - y0[p] + dy[p] - 1) / dy[p];
+            a->stride[p] = (uint32_t)(((uint64_t)a->pw[p] * a->bits + 7) / 8);
+            off += (uint64_t)a->ph[p] * a->stride[p];
+        } else {
+            a->stride[p] = 1; // never addressed
+        }
+    }
+    a->base[7] = off;
+    return true;
+}
+
+int oxi_interlace_image(const oxi_ihdr *h, const uint8_t *data, size_t len, uint8_t *out, size_t *out_len) {
+    if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
+    Adam7 a;
+    make_adam7(h, &a);
+    if (len < (size_t)a.full_stride * h->height) return fail(OXI_E_ARG, "data shorter than the progressive image");
+    Call call(data, len, a.base[7]);
+    if (!call.ok()) return call.err;
+    k_interlace<<<grid_for(a.base[7], call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, a);
+    if (int rc = call.check("k_interlace")) return rc;
+    if (int rc = call.download(out, a.base[7])) return rc;
+    if (out_len) *out_len = a.base[7];
+    return OXI_OK;
+}
+
+int oxi_deinterlace_image(const oxi_ihdr *h, const uint8_t *data, size_t len, uint8_t *out, size_t *out_len) {
+    if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
+    Adam7 a;
+    make_adam7(h, &a);
+    if (len < a.base[7]) return fail(OXI_E_ARG, "data shorter than the interlaced image");
+    const size_t total = (size_t)a.full_stride * h->height;
+    Call call(data, len, total);
+    if (!call.ok()) return call.err;
+    k_deinterlace<<<grid_for(total, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, a);
+    if (int rc = call.check("k_deinterlace")) return rc;
+    if (int rc = call.download(out, total)) return rc;
+    if (out_len) *out_len = total;
+    return OXI_OK;
+}
+
+
+int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, uint8_t *out, size_t *out_len) {
+    if (!valid_ihdr(h) || !filtered || !out) return fail(OXI_E_ARG, "bad arguments");
+    // geometry of the unfiltered data this stream holds: every scanline carries one extra byte
+    // (ScanLines with has_filter = true, png/scan_lines.rs:159-163)
+    Geom g;
+    size_t lo = 0, hi = len; // find data_len such that data_len + rows(data_len) is the largest value <= len
+    if (!build_geom(h, len, 0, &g)) return fail(OXI_E_ARG, "invalid IHDR");
+    while (lo < hi) {
+        const size_t mid = lo + (hi - lo + 1) / 2;
+        build_geom(h, mid, 0, &g);
+        if (g.out_len <= len) lo = mid; else hi = mid - 1;
+    }
+    build_geom(h, lo, 0, &g);
+    if (g.total_rows == 0) { if (out_len) *out_len = 0; return OXI_OK; }
+    Call call(filtered, len, g.data_len);
+    if (!call.ok()) return call.err;
+    const uint64_t items = g.n_pass;
+    k_unfilter<<<(unsigned)((items * 32 + 127) / 128), 128, 0, call.s->stream>>>(g, call.d_in, call.d_out, 1, len, call.st);
+    if (int rc = call.check("k_unfilter")) return rc;
+    ScanState st;
+    if (int rc = call.state(&st)) return rc;
+    if (st.fail) return fail(OXI_E_DATA, "invalid filter type byte (PngError::InvalidData)");
+    if (int rc = call.download(out, g.data_len)) return rc;
+    if (out_len) *out_len = g.data_len;
     return OXI_OK;
 }
 

@@ -265,3 +265,50 @@ def filter_tier(png: PngImage, strategy: FilterStrategy, optimize_alpha: bool) -
     h = png.ihdr._c()
     s, _keep = strategy._c()
     return lib().oxi_filter_tier(C.byref(h), png.data.size, C.byref(s), int(optimize_alpha)).decode()
+
+
+# ---- the steps either side of the hot path -----------------------------------------------------------
+
+def unfilter_image(ihdr: IhdrData, filtered) -> np.ndarray:
+    """PngImage::unfilter_image (png/mod.rs:335-351): inflated IDAT stream -> PngImage.data.  Raises ValueError for an
+    invalid filter-type byte (the reference's PngError::InvalidData)."""
+    f = _u8(filtered)
+    h = ihdr._c()
+    out = np.empty(f.size + 16, dtype=np.uint8)
+    n = C.c_size_t(0)
+    rc = lib().oxi_unfilter_image(C.byref(h), C.c_void_p(f.ctypes.data), C.c_size_t(f.size), C.c_void_p(out.ctypes.data),
+                                  C.byref(n))
+    if rc == -5:
+        raise ValueError("invalid filter type byte")
+    check(rc, "oxi_unfilter_image")
+    return out[:n.value]
+
+
+def interlace_image(png: PngImage) -> PngImage:
+    """interlace_image (interlace.rs:6-60): progressive -> Adam7 layout."""
+    h = png.ihdr._c()
+    out = np.empty(png.data.size + 8 * png.ihdr.height + 64, dtype=np.uint8)
+    n = C.c_size_t(0)
+    check(lib().oxi_interlace_image(C.byref(h), C.c_void_p(png.data.ctypes.data), C.c_size_t(png.data.size),
+                                    C.c_void_p(out.ctypes.data), C.byref(n)), "oxi_interlace_image")
+    i = png.ihdr
+    return PngImage(IhdrData(i.width, i.height, i.color_type, i.bit_depth, True), out[:n.value])
+
+
+def deinterlace_image(png: PngImage) -> PngImage:
+    """deinterlace_image (interlace.rs:62-150): Adam7 -> progressive layout."""
+    h = png.ihdr._c()
+    i = png.ihdr
+    stride = (i.width * i.bpp() + 7) // 8
+    out = np.empty(stride * i.height + 16, dtype=np.uint8)
+    n = C.c_size_t(0)
+    check(lib().oxi_deinterlace_image(C.byref(h), C.c_void_p(png.data.ctypes.data), C.c_size_t(png.data.size),
+                                      C.c_void_p(out.ctypes.data), C.byref(n)), "oxi_deinterlace_image")
+    return PngImage(IhdrData(i.width, i.height, i.color_type, i.bit_depth, False), out[:n.value])
+
+
+def change_interlacing(png: PngImage, interlace: bool) -> Optional[PngImage]:
+    """PngImage::change_interlacing (png/mod.rs:272-284): None when the image already has that layout."""
+    if interlace == png.ihdr.interlaced:
+        return None
+    return interlace_image(png) if interlace else deinterlace_image(png)

@@ -1,0 +1,61 @@
+"""GPU parity of the SURVEY 8f "next" rows: unfilter_image and Adam7 interlace / deinterlace (bit-exact vs the oracle)."""
+import numpy as np
+import pytest
+
+import helpers
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+FORMATS = [(0, 1), (0, 2), (3, 4), (0, 8), (3, 8), (4, 8), (2, 8), (6, 8), (0, 16), (4, 16), (2, 16), (6, 16)]
+SHAPES = [(1, 1), (1, 9), (2, 2), (3, 5), (5, 3), (8, 8), (9, 17), (33, 7), (40, 70), (257, 65)]
+
+
+def test_interlace_and_deinterlace_match_oracle():
+    import oxipng_b200 as ox
+    for ct, bd in FORMATS:
+        for (w, h) in SHAPES:
+            ih, d = helpers.synth_image(w, h, ct, bd, 7 + w, "random")
+            img = helpers.product_image(ih, d)
+            want = oracle.interlace_image(ih, d)
+            got = ox.interlace_image(img)
+            assert got.ihdr.interlaced and np.array_equal(got.data, want), (ct, bd, w, h)
+            back = ox.deinterlace_image(got)
+            assert not back.ihdr.interlaced and np.array_equal(back.data, d), (ct, bd, w, h)
+            assert np.array_equal(back.data, oracle.deinterlace_image((w, h, ct, bd, 1), want))
+            assert ox.change_interlacing(img, False) is None and ox.change_interlacing(got, True) is None
+
+
+def test_unfilter_inverts_every_strategy_and_matches_oracle():
+    import oxipng_b200 as ox
+    for ct, bd in FORMATS:
+        for il in (False, True):
+            for (w, h) in [(1, 1), (3, 5), (9, 17), (40, 70), (257, 65)]:
+                ih, d = helpers.synth_image(w, h, ct, bd, 11 + h, "photo" if w > 8 else "random", il)
+                hdr = helpers.product_image(ih, d).ihdr
+                for name, kind, basic in helpers.STRATEGIES:
+                    filtered, _, _ = oracle.filter_image(ih, d, kind, basic)
+                    got = ox.unfilter_image(hdr, filtered)
+                    assert np.array_equal(got, d), (ct, bd, il, w, h, name)
+                    assert np.array_equal(got, oracle.unfilter_image(ih, filtered))
+
+
+def test_unfilter_golden_fixtures(golden):
+    """the reference's own files: stream as stored in the PNG (whatever filters its encoder chose) -> pixels"""
+    import oxipng_b200 as ox
+    for c in golden:
+        hdr = helpers.product_image(c.ihdr, c.data, c.palette, c.trns).ihdr
+        filtered, _, _ = oracle.filter_image(c.ihdr, c.data, oracle.ENTROPY, 0)
+        assert np.array_equal(ox.unfilter_image(hdr, filtered), c.data), c.name
+
+
+def test_unfilter_rejects_bad_filter_byte():
+    import oxipng_b200 as ox
+    ih, d = helpers.synth_image(16, 4, 2, 8, 1, "random")
+    filtered, _, _ = oracle.filter_image(ih, d, oracle.BASIC, 1)
+    filtered = filtered.copy()
+    filtered[49] = 9  # second row's filter byte
+    with pytest.raises(ValueError):
+        ox.unfilter_image(helpers.product_image(ih, d).ihdr, filtered)
+    with pytest.raises(ValueError):
+        oracle.unfilter_image(ih, filtered)
