@@ -171,3 +171,51 @@ def test_fast_tier_batch_many_images():
         want = [oracle.filter_image(ih, d, kind, basic) for _, d in imgs]
         assert np.array_equal(used[j], np.concatenate([w[1] for w in want])), j
         assert np.array_equal(outs[j], np.concatenate([w[0] for w in want])), j
+
+
+def test_concurrent_host_threads():
+    """filter_image is called concurrently from rayon workers on one shared image (evaluate.rs:141-153): many host threads
+    through the host-buffer C ABI at once, every result bit-exact."""
+    import concurrent.futures as cf
+    import oxipng_b200 as ox
+    ih, d = helpers.synth_image(300, 64, 6, 8, 31, "photo")
+    img = helpers.product_image(ih, d)
+    want = {n: oracle.filter_image(ih, d, k, b) for n, k, b in helpers.STRATEGIES}
+
+    def work(i):
+        n = helpers.STRATEGIES[i % len(helpers.STRATEGIES)][0]
+        out, st = img.filter_image(helpers.product_strategy(n), False)
+        return n, out
+
+    with cf.ThreadPoolExecutor(max_workers=12) as ex:
+        for n, out in ex.map(work, range(96)):
+            assert np.array_equal(out, want[n][0]), n
+
+
+def test_repeatability_stress():
+    """The fast kernels run with as few CTA-wide barriers as the data hazards allow; a missed hazard would show up as
+    run-to-run differences or as a mismatch on some image of a larger batch.  (compute-sanitizer is closed on this pool.)"""
+    import oxipng_b200 as ox
+    n = 48
+    for (w, h, ct, bd, kind) in [(512, 40, 6, 8, "photo"), (300, 33, 2, 8, "photo"), (1024, 12, 6, 16, "random")]:
+        imgs = [helpers.synth_image(w, h, ct, bd, 5000 + i, kind if i % 4 else "random") for i in range(n)]
+        ih = imgs[0][0]
+        hdr = helpers.product_image(ih, imgs[0][1]).ihdr
+        data = np.concatenate([d for _, d in imgs])
+        strat = [ox.FilterStrategy.NONE, ox.FilterStrategy.Bigrams, ox.FilterStrategy.BigEnt, ox.FilterStrategy.MinSum,
+                 ox.FilterStrategy.Entropy]
+        kinds = [(oracle.BASIC, 0), (oracle.BIGRAMS, 0), (oracle.BIGENT, 0), (oracle.MINSUM, 0), (oracle.ENTROPY, 0)]
+        first = None
+        for rep in range(4):
+            for group in ([0, 1, 2], [3], [4]):
+                outs, used = ox.filter_batch(hdr, data, n, [strat[g] for g in group], False)
+                key = tuple(helpers.sha(o) for o in outs) + tuple(helpers.sha(u) for u in used)
+                if rep == 0:
+                    for g, o, u in zip(group, outs, used):
+                        want = [oracle.filter_image(ih, d, *kinds[g]) for _, d in imgs]
+                        assert np.array_equal(u, np.concatenate([x[1] for x in want])), (w, h, g)
+                        assert np.array_equal(o, np.concatenate([x[0] for x in want])), (w, h, g)
+                    first = first or {}
+                    first[tuple(group)] = key
+                else:
+                    assert key == first[tuple(group)], ("run-to-run difference", w, h, group, rep)
