@@ -600,14 +600,17 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
 // ---- writing the chosen row --------------------------------------------------------------------------------------
 // out_row points at the filter-type byte of this row in the filtered stream.  Interior 16-byte granules of the
 // output are produced in the output's alignment frame; the (at most 31) edge bytes are written one by one.
+// `rot` rotates the thread->granule assignment so that the write passes of several strategies of one row land on
+// different warps (a 4 KB row has 256 granules: 8 of the 32 warps of a 1024-thread CTA).
 template <int NT>
 __device__ __forceinline__ void write_row(int f, const uint8_t *cur, const uint8_t *up, uint32_t len, int bpp,
-                                          uint8_t *out_row) {
+                                          uint8_t *out_row, int rot = 0) {
+    const int tid_r = ((int)threadIdx.x - rot) & (NT - 1);
     const int phase = (int)(reinterpret_cast<uintptr_t>(out_row) & 15u);
     const int total = (int)len + 1;                 // stream positions p = 0..len
     const int q_full_end = (total + phase) >> 4;    // granules [1, q_full_end) are complete and hold residuals only
     uint8_t *base = out_row - phase;
-    for (int q = 1 + (int)threadIdx.x; q < q_full_end; q += NT) {
+    for (int q = 1 + tid_r; q < q_full_end; q += NT) {
         const int i0 = 16 * q - phase - 1; // row byte of the granule's first position (>= 0)
         const uint4 x = ld_unaligned16(cur + i0);
         uint4 r;
@@ -634,7 +637,7 @@ __device__ __forceinline__ void write_row(int f, const uint8_t *cur, const uint8
     const int head_end = min(16 - phase, total);
     const int tail_begin = max(16 * q_full_end - phase, head_end);
     const int n_edge = head_end + (total - tail_begin);
-    for (int e = threadIdx.x; e < n_edge; e += NT) {
+    for (int e = tid_r; e < n_edge; e += NT) {
         const int p = e < head_end ? e : tail_begin + (e - head_end);
         out_row[p] = p == 0 ? (uint8_t)f : (uint8_t)residual_at(f, cur, up, p - 1, bpp);
     }
@@ -824,7 +827,8 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_BIGRAM) ? 1 : (SC ==
                         }
                     }
                 }
-                write_row<NT>(f, cur, up, len, bpp, st.out + img * P.g.out_len + in_off + r);
+                write_row<NT>(f, cur, up, len, bpp, st.out + img * P.g.out_len + in_off + r,
+                              (int)((j2 * ((((len + 16) >> 4) + 31) & ~31u)) & (NT - 1)));
                 if (tid == 0) st.filters_used[img * P.g.total_rows + r] = (uint8_t)f;
             }
             if (row_end_barrier) __syncthreads(); // slot `sp` may be refilled by the next iteration's prefetch
