@@ -1,0 +1,49 @@
+"""The evaluate.rs trial dispatch over the fused GPU call picks the same candidate as the same flow driven by the oracle."""
+import zlib
+
+import numpy as np
+import pytest
+
+import helpers
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_evaluator_matches_oracle_driven_flow():
+    import oxipng_b200 as ox
+    from oxipng_b200 import reduction as R
+    from oxipng_b200.evaluate import Evaluator, key_chunks_size
+    rng = np.random.default_rng(4)
+    pal = rng.integers(0, 256, size=(40, 4), dtype=np.uint8)
+    pal[:, 3] = 255
+    idx = np.kron(rng.integers(0, 40, size=(20, 30)), np.ones((8, 8), dtype=np.int64))
+    rgba = helpers.product_image((240, 160, 6, 8, 0), np.ascontiguousarray(pal[idx]).reshape(-1))
+    cands = [rgba, R.reduced_alpha_channel(rgba, False), R.reduced_to_indexed(rgba, True)]
+    assert all(c is not None for c in cands)
+    S = ox.FilterStrategy
+    filters = [S.NONE, S.SUB, S.Entropy, S.Bigrams]  # the reference's default set (options.rs:282-287)
+    ev = Evaluator(filters, zlib_level=6, optimize_alpha=False, final_round=True)
+    for c in cands:
+        ev.try_image(c)
+    best = ev.get_best_candidate()
+    # the same flow with the CPU oracle doing the filtering
+    table = {"None": (oracle.BASIC, 0), "Sub": (oracle.BASIC, 1), "Entropy": (oracle.ENTROPY, 0), "Bigrams": (oracle.BIGRAMS, 0)}
+    want = None
+    best_size = None
+    for nth, c in enumerate(cands):
+        ih = (c.ihdr.width, c.ihdr.height, c.ihdr.color_type.code, int(c.ihdr.bit_depth), int(c.ihdr.interlaced))
+        for fi, f in enumerate(filters):
+            out, used, _ = oracle.filter_image(ih, c.data, *table[str(f)])
+            est = len(zlib.compress(out.tobytes(), 6)) + key_chunks_size(c)
+            if best_size is not None and est > best_size:
+                continue
+            best_size = est if best_size is None else min(best_size, est)
+            key = (est, c.data.size, fi, -nth)
+            if want is None or key < want[0]:
+                want = (key, nth, str(f), used)
+    assert best.nth == want[1] and str(best.filter) == want[2] and best.estimated_output_size == want[0][0]
+    if best.filter_used.kind == "Predefined":
+        assert list(best.filter_used.lines) == want[3].tolist()
+    assert best.image is cands[2]  # the indexed candidate wins on this 40-colour image
+    assert zlib.decompress(best.idat_data)[0] in (0, 1, 2, 3, 4)
