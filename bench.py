@@ -34,6 +34,16 @@ ROWS = IMG_H                              # S
 SEED0 = 0xB2000005
 
 
+# stdout carries exactly ONE JSON line: everything else written to fd 1 (NCCL's version banner, library chatter) is
+# redirected to stderr, and the result line goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -88,7 +98,7 @@ def run_reference(args):
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, images_this_step=None):
@@ -352,7 +362,7 @@ def run_ours(args):
         }
         if others is not None:
             line["other_configs"] = others
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
