@@ -252,7 +252,10 @@ template <int D, int NT>
 __device__ __forceinline__ void entropy_pass(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
                                              uint32_t *hist) {
     const uint32_t nchunks = (len + 15) >> 4;
-    uint32_t *h = hist + (threadIdx.x & (HIST_REP - 1)) * 256;
+    // replica by lane; the bins of replica k are stored at bin ^ 8k: the replicas' bases are multiples of 256 words, so
+    // without the rotation the copies of one hot bin would all sit in the same bank
+    const uint32_t rep = threadIdx.x & (HIST_REP - 1), rotw = rep * 0x08080808u;
+    uint32_t *h = hist + rep * 256;
     for (uint32_t c = threadIdx.x; c < nchunks; c += NT) {
         const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
         const int valid = (int)len - (int)(16 * c);
@@ -261,11 +264,11 @@ __device__ __forceinline__ void entropy_pass(const uint8_t *cur, const uint8_t *
             const uint32_t x = cw.w[k + 2], u = uw.w[k + 2], l = left_word<D>(cw, k, shift), ul = left_word<D>(uw, k, shift);
             const int nv = valid - 4 * k;
             if (nv <= 0) break;
-            hist_add4(h + 0 * HIST_REP * 256, x, nv);
-            hist_add4(h + 1 * HIST_REP * 256, __vsub4(x, l), nv);
-            hist_add4(h + 2 * HIST_REP * 256, __vsub4(x, u), nv);
-            hist_add4(h + 3 * HIST_REP * 256, __vsub4(x, __vhaddu4(l, u)), nv);
-            hist_add4(h + 4 * HIST_REP * 256, __vsub4(x, paeth4(l, u, ul)), nv);
+            hist_add4(h + 0 * HIST_REP * 256, x ^ rotw, nv);
+            hist_add4(h + 1 * HIST_REP * 256, __vsub4(x, l) ^ rotw, nv);
+            hist_add4(h + 2 * HIST_REP * 256, __vsub4(x, u) ^ rotw, nv);
+            hist_add4(h + 3 * HIST_REP * 256, __vsub4(x, __vhaddu4(l, u)) ^ rotw, nv);
+            hist_add4(h + 4 * HIST_REP * 256, __vsub4(x, paeth4(l, u, ul)) ^ rotw, nv);
         }
     }
 }
@@ -274,12 +277,12 @@ template <int NT>
 __device__ __forceinline__ void entropy_score(uint32_t *hist, uint32_t *s_ent) {
     for (uint32_t idx = threadIdx.x; idx < 5 * 256; idx += NT) {
         const uint32_t f = idx >> 8, v = idx & 255u;
-        uint32_t *h = hist + f * HIST_REP * 256 + v;
+        uint32_t *h = hist + f * HIST_REP * 256;
         uint32_t cnt = (v == f) ? 1u : 0u; // the filter-type byte that leads the filtered line
 #pragma unroll
-        for (int r = 0; r < HIST_REP; r++) {
-            cnt += h[r * 256];
-            h[r * 256] = 0;
+        for (int r = 0; r < HIST_REP; r++) { // replica r keeps bin v at v ^ 8r
+            cnt += h[r * 256 + (v ^ (uint32_t)(8 * r))];
+            h[r * 256 + (v ^ (uint32_t)(8 * r))] = 0;
         }
         uint32_t s = warp_sum(cnt ? ilog2i(cnt) : 0u);
         if ((threadIdx.x & 31) == 0) atomicAdd(&s_ent[f], s);
