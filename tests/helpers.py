@@ -147,3 +147,95 @@ def synth_image(width: int, height: int, ct: int, bd: int, seed: int, kind: str 
         data = oracle.interlace_image(ihdr, data)
         ihdr = (width, height, ct, bd, 1)
     return ihdr, data
+
+
+# ---- oracle-backed adapters with the product's names (for end-to-end flow parity tests) ------------------------------
+
+def _img_tuple(png):
+    i = png.ihdr
+    return (i.width, i.height, i.color_type.code, int(i.bit_depth), int(i.interlaced))
+
+
+def _from_oracle(r):
+    if r is None:
+        return None
+    return product_image(tuple(r["ihdr"]), r["data"], r.get("palette"), r.get("trns"))
+
+
+class OracleReductions:
+    """oxipng_b200.reduction's interface implemented with the CPU oracle (tests only)."""
+
+    @staticmethod
+    def _pt(png):
+        ct = png.ihdr.color_type
+        pal = ct.palette_array() if ct.code == 3 else None
+        return _img_tuple(png), png.data, pal, ct.transparent
+
+    def cleaned_alpha_channel(self, png):
+        ih, d, _, _ = self._pt(png)
+        r = oracle.cleaned_alpha_channel(ih, d)
+        return None if r is None else product_image(ih, r["data"])
+
+    def reduced_alpha_channel(self, png, oa):
+        ih, d, _, _ = self._pt(png)
+        return _from_oracle(oracle.reduced_alpha_channel(ih, d, oa))
+
+    def reduced_bit_depth_16_to_8(self, png, fs):
+        ih, d, pal, t = self._pt(png)
+        return _from_oracle(oracle.reduced_bit_depth_16_to_8(ih, d, fs, trns=t))
+
+    def reduced_rgb_to_grayscale(self, png):
+        ih, d, _, t = self._pt(png)
+        return _from_oracle(oracle.reduced_rgb_to_grayscale(ih, d, t if ih[2] == 2 else None))
+
+    def expanded_bit_depth_to_8(self, png):
+        ih, d, pal, t = self._pt(png)
+        return _from_oracle(oracle.expanded_bit_depth_to_8(ih, d, pal, t if ih[2] == 0 else None))
+
+    def reduced_palette(self, png, oa):
+        ih, d, pal, _ = self._pt(png)
+        if ih[2] != 3:
+            return None
+        return _from_oracle(oracle.reduced_palette(ih, d, pal, oa))
+
+    def sorted_palette(self, png):
+        ih, d, pal, _ = self._pt(png)
+        if ih[2] != 3:
+            return None
+        return _from_oracle(oracle.sorted_palette(ih, d, pal))
+
+    def reduced_to_indexed(self, png, ag):
+        ih, d, _, t = self._pt(png)
+        return _from_oracle(oracle.reduced_to_indexed(ih, d, ag, t))
+
+    def reduced_bit_depth_8_or_less(self, png):
+        ih, d, pal, t = self._pt(png)
+        return _from_oracle(oracle.reduced_bit_depth_8_or_less(ih, d, pal, t if ih[2] == 0 else None))
+
+    def indexed_to_channels(self, png, ag, oa):
+        ih, d, pal, _ = self._pt(png)
+        if ih[2] != 3:
+            return None
+        return _from_oracle(oracle.indexed_to_channels(ih, d, pal, ag, oa))
+
+
+def oracle_change_interlacing(png, interlace):
+    if interlace == png.ihdr.interlaced:
+        return None
+    ih = _img_tuple(png)
+    ct = png.ihdr.color_type
+    data = oracle.interlace_image(ih, png.data) if interlace else oracle.deinterlace_image(ih, png.data)
+    return product_image((ih[0], ih[1], ih[2], ih[3], int(interlace)), data,
+                         ct.palette_array() if ct.code == 3 else None, ct.transparent)
+
+
+class RecordingEvaluator:
+    """Stands in for Evaluator in flow tests: records what perform_reductions submits, in order."""
+
+    def __init__(self):
+        self.tried = []
+
+    def try_image(self, png, description=""):
+        self.tried.append((description, _img_tuple(png), sha(png.data),
+                           sha(png.ihdr.color_type.palette_array()) if png.ihdr.color_type.code == 3 else None,
+                           png.ihdr.color_type.transparent))
