@@ -219,3 +219,38 @@ def test_repeatability_stress():
                     first[tuple(group)] = key
                 else:
                     assert key == first[tuple(group)], ("run-to-run difference", w, h, group, rep)
+
+
+def test_rows_beyond_the_fast_tier_fall_back_to_generic():
+    """Rows that do not fit the shared-memory ring (here 120 KB and 160 KB per row) take the generic tier by themselves."""
+    import oxipng_b200 as ox
+    for (w, h, ct, bd) in [(30000, 3, 6, 8), (20000, 2, 6, 16)]:
+        ih, d = helpers.synth_image(w, h, ct, bd, 77, "photo")
+        img = helpers.product_image(ih, d)
+        assert ox.filter_tier(img, ox.FilterStrategy.MinSum, False) == "generic"
+        _check(ih, d, alphas=(False,), strategies=["Sub", "Paeth", "MinSum", "Entropy", "Bigrams", "BigEnt"], label=f"huge/{w}")
+    # 40 KB rows: fast tier for MinSum/Entropy, generic for the bigram scorers (table + ring exceed shared memory)
+    ih, d = helpers.synth_image(10000, 3, 6, 8, 78, "photo")
+    img = helpers.product_image(ih, d)
+    assert ox.filter_tier(img, ox.FilterStrategy.MinSum, False) == "fast"
+    assert ox.filter_tier(img, ox.FilterStrategy.BigEnt, False) == "generic"
+    _check(ih, d, alphas=(False,), strategies=["MinSum", "Entropy", "Bigrams", "BigEnt"], label="40KB rows")
+
+
+def test_argument_errors_are_reported():
+    import ctypes as C
+    import oxipng_b200 as ox
+    from oxipng_b200 import _lib
+    L = ox.lib()
+    h = _lib.CIhdr(4, 4, 6, 8, 0)
+    d = np.zeros(64, np.uint8)
+    out = np.zeros(80, np.uint8)
+    used = np.zeros(4, np.uint8)
+    bad = _lib.CStrategy(9, 0, None, 0)
+    assert L.oxi_filter_image(C.byref(h), d.ctypes.data, 64, C.byref(bad), 0, out.ctypes.data, used.ctypes.data, None) == -1
+    bad = _lib.CStrategy(0, 7, None, 0)
+    assert L.oxi_filter_image(C.byref(h), d.ctypes.data, 64, C.byref(bad), 0, out.ctypes.data, used.ctypes.data, None) == -1
+    assert b"strategy" in L.oxi_last_error()
+    # empty image data: nothing to do, no rows
+    ok = _lib.CStrategy(1, 0, None, 0)
+    assert L.oxi_filter_image(C.byref(h), d.ctypes.data, 0, C.byref(ok), 0, out.ctypes.data, used.ctypes.data, None) == 0
