@@ -561,28 +561,46 @@ __global__ void __launch_bounds__(RT) k_deinterlace(const uint8_t *__restrict__ 
 
 // ---- unfilter_image (png/mod.rs:335-351, filters/mod.rs:188-239), SURVEY 8f row 1 ----------------------------------
 // Reconstruction is a recurrence along the row (Sub/Average/Paeth use the rebuilt left pixel) and across rows
-// (Up/Average/Paeth use the rebuilt previous row).  One warp takes one (image, pass) and walks it in tiles of 32
-// rows in skewed lockstep: at step s lane l rebuilds pixel s-l of row k0+l, so the pixel above it (lane l-1) was
+// (Up/Average/Paeth use the rebuilt previous row).  A warp takes a tile of 32 rows and walks it in skewed lockstep: at step s lane l rebuilds pixel s-l of row k0+l, so the pixel above it (lane l-1) was
 // finished in the step before and arrives by shuffle, "upleft" is the value shuffled in one step earlier and "left"
-// never leaves the lane's registers.  Parallelism: 32 rows per warp, warps over images and Adam7 passes.
+// never leaves the lane's registers.
 __device__ __forceinline__ uint32_t paeth4_u(uint32_t a, uint32_t b, uint32_t c) { // byte-wise paeth_predictor
     uint32_t r = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) r |= paeth((a >> (8 * j)) & 255u, (b >> (8 * j)) & 255u, (c >> (8 * j)) & 255u) << (8 * j);
     return r;
 }
-__device__ __forceinline__ uint32_t ld_bytes(const uint8_t *p, int n) { // n <= 4 bytes, little endian
-    uint32_t v = 0;
-    for (int j = 0; j < n; j++) v |= (uint32_t)p[j] << (8 * j);
-    return v;
+// n <= 4 bytes at any alignment, little endian: two aligned 32-bit loads + funnel shift (the second word is only read
+// when the bytes straddle it; buffers carry >= 4 bytes of slack).  CG = bypass L1 (data written by another warp).
+template <bool CG>
+__device__ __forceinline__ uint32_t ld_bytes(const uint8_t *p, int n) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p - mis);
+    const uint32_t w0 = CG ? __ldcg(q) : *q;
+    uint32_t w1 = 0;
+    if (mis + n > 4) w1 = CG ? __ldcg(q + 1) : q[1];
+    const uint32_t v = __funnelshift_r(w0, w1, 8 * mis);
+    return n >= 4 ? v : (v & ((1u << (8 * n)) - 1u));
 }
 __device__ __forceinline__ void st_bytes(uint8_t *p, uint32_t v, int n) {
-    for (int j = 0; j < n; j++) p[j] = (uint8_t)(v >> (8 * j));
+    if (n == 4 && (reinterpret_cast<uintptr_t>(p) & 3u) == 0) {
+        *reinterpret_cast<uint32_t *>(p) = v;
+    } else {
+        for (int j = 0; j < n; j++) p[j] = (uint8_t)(v >> (8 * j));
+    }
 }
-__global__ void __launch_bounds__(128) k_unfilter(Geom g, const uint8_t *__restrict__ in, uint8_t *out, uint64_t n_images,
-                                                   uint64_t in_stride, ScanState *st) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t item = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// One CTA per (image, pass); its warps take the 32-row tiles round-robin and run them as a pipeline: the warp of
+// tile t trails the warp of tile t-1 by 32 steps, because row 32t-1 (the row above its first row) is produced by lane
+// 31 of that warp.  Progress is published in shared memory every UF_CHUNK steps; the boundary row itself goes through
+// global memory (stores are fenced before the progress word is updated, the reader bypasses L1 with ld.global.cg).
+constexpr int UF_WARPS = 32, UF_CHUNK = 32;
+__global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_t *__restrict__ in, uint8_t *out,
+                                                            uint64_t n_images, uint64_t in_stride, ScanState *st) {
+    __shared__ unsigned long long progress[UF_WARPS]; // (tile << 32) | steps finished, per warp
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) progress[warp] = 0;
+    __syncthreads();
+    const uint64_t item = blockIdx.x;
     if (item >= n_images * g.n_pass) return;
     const uint64_t img = item / g.n_pass;
     const PassDesc pd = g.pass[item % g.n_pass];
@@ -591,47 +609,60 @@ __global__ void __launch_bounds__(128) k_unfilter(Geom g, const uint8_t *__restr
     // filtered stream: row r of the image starts at in_base + r (one filter byte per earlier row), then 1 + len bytes
     const uint8_t *src = in + img * in_stride + pd.in_base + pd.row0;
     uint8_t *dst = out + img * g.data_len + pd.in_base;
-    for (uint32_t k0 = 0; k0 < pd.nrows; k0 += 32) {
-        const uint32_t k = k0 + lane;
+    const uint32_t ntiles = (pd.nrows + 31) / 32, steps = npix + 31;
+    volatile unsigned long long *vprog = progress;
+    for (uint32_t t = warp; t < ntiles; t += UF_WARPS) {
+        const uint32_t k = t * 32 + lane;
         const bool valid = k < pd.nrows;
         const uint8_t *frow = src + (uint64_t)k * (len + 1);
         uint8_t *orow = dst + (uint64_t)k * len;
         uint32_t f = valid ? frow[0] : 0;
         if (f > 4) { st->fail = 1; f = 0; } // RowFilter::try_from fails -> PngError::InvalidData
-        const uint8_t *uprow = (lane == 0 && k > 0) ? orow - len : nullptr; // rebuilt by the previous tile (or zeros)
+        const uint8_t *uprow = (lane == 0 && k > 0) ? orow - len : nullptr; // last row of tile t-1 (or zeros for row 0)
+        const uint32_t pw = (t + UF_WARPS - 1) % UF_WARPS;                // warp that runs tile t-1
         uint32_t l0 = 0, l1 = 0, u0 = 0, u1 = 0; // left pixel (own last result), up pixel of the previous step
-        const uint32_t steps = npix + 31;
-        for (uint32_t s = 0; s < steps; s++) {
-            // pixel above: the lane above finished it in the previous step
-            uint32_t a0 = __shfl_up_sync(0xffffffffu, l0, 1), a1 = __shfl_up_sync(0xffffffffu, l1, 1);
-            const int x = (int)s - (int)lane;
-            const bool act = valid && x >= 0 && x < (int)npix;
-            if (lane == 0) {
-                a0 = a1 = 0;
-                if (uprow && act) {
-                    a0 = ld_bytes(uprow + (size_t)x * bpp, n0);
-                    if (n1) a1 = ld_bytes(uprow + (size_t)x * bpp + 4, n1);
-                }
+        for (uint32_t s0 = 0; s0 < steps; s0 += UF_CHUNK) {
+            const uint32_t s1 = min(s0 + UF_CHUNK, steps);
+            if (t > 0) { // lane 0 reads pixels [s0, s1) of row 32t-1: finished by tile t-1 at its step x + 32
+                const unsigned long long need = ((unsigned long long)(t - 1) << 32) | min(s1 + 31, steps);
+                while (vprog[pw] < need) {}
+                __syncwarp();
             }
-            if (act) {
-                const uint32_t d0 = ld_bytes(frow + 1 + (size_t)x * bpp, n0);
-                const uint32_t d1 = n1 ? ld_bytes(frow + 1 + (size_t)x * bpp + 4, n1) : 0u;
-                uint32_t p0, p1;
-                switch (f) {
-                case 0: p0 = p1 = 0; break;
-                case 1: p0 = l0; p1 = l1; break;
-                case 2: p0 = a0; p1 = a1; break;
-                case 3: p0 = __vhaddu4(l0, a0); p1 = __vhaddu4(l1, a1); break;
-                default: p0 = paeth4_u(l0, a0, u0); p1 = n1 ? paeth4_u(l1, a1, u1) : 0u; break;
+            for (uint32_t s = s0; s < s1; s++) {
+                // pixel above: the lane above finished it in the previous step
+                uint32_t a0 = __shfl_up_sync(0xffffffffu, l0, 1), a1 = __shfl_up_sync(0xffffffffu, l1, 1);
+                const int x = (int)s - (int)lane;
+                const bool act = valid && x >= 0 && x < (int)npix;
+                if (lane == 0) {
+                    a0 = a1 = 0;
+                    if (uprow && act) {
+                        const uint8_t *u = uprow + (size_t)x * bpp;
+                        a0 = ld_bytes<true>(u, n0);
+                        if (n1) a1 = ld_bytes<true>(u + 4, n1);
+                    }
                 }
-                const uint32_t r0 = __vadd4(d0, p0), r1 = __vadd4(d1, p1);
-                st_bytes(orow + (size_t)x * bpp, r0, n0);
-                if (n1) st_bytes(orow + (size_t)x * bpp + 4, r1, n1);
-                l0 = r0; l1 = r1;
+                if (act) {
+                    const uint32_t d0 = ld_bytes<false>(frow + 1 + (size_t)x * bpp, n0);
+                    const uint32_t d1 = n1 ? ld_bytes<false>(frow + 1 + (size_t)x * bpp + 4, n1) : 0u;
+                    uint32_t p0, p1;
+                    switch (f) {
+                    case 0: p0 = p1 = 0; break;
+                    case 1: p0 = l0; p1 = l1; break;
+                    case 2: p0 = a0; p1 = a1; break;
+                    case 3: p0 = __vhaddu4(l0, a0); p1 = __vhaddu4(l1, a1); break;
+                    default: p0 = paeth4_u(l0, a0, u0); p1 = n1 ? paeth4_u(l1, a1, u1) : 0u; break;
+                    }
+                    const uint32_t r0 = __vadd4(d0, p0), r1 = __vadd4(d1, p1);
+                    st_bytes(orow + (size_t)x * bpp, r0, n0);
+                    if (n1) st_bytes(orow + (size_t)x * bpp + 4, r1, n1);
+                    l0 = r0; l1 = r1;
+                }
+                u0 = a0; u1 = a1; // becomes "upleft" of the next step
             }
-            u0 = a0; u1 = a1; // becomes "upleft" of the next step
+            __threadfence_block(); // this chunk's pixels are visible before the progress word says so
+            __syncwarp();
+            if (lane == 0) vprog[warp] = ((unsigned long long)t << 32) | s1;
         }
-        __syncwarp(); // the next tile's first row reads the last row of this one
     }
 }
 
@@ -1197,8 +1228,7 @@ int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, u
     if (g.total_rows == 0) { if (out_len) *out_len = 0; return OXI_OK; }
     Call call(filtered, len, g.data_len);
     if (!call.ok()) return call.err;
-    const uint64_t items = g.n_pass;
-    k_unfilter<<<(unsigned)((items * 32 + 127) / 128), 128, 0, call.s->stream>>>(g, call.d_in, call.d_out, 1, len, call.st);
+    k_unfilter<<<g.n_pass, UF_WARPS * 32, 0, call.s->stream>>>(g, call.d_in, call.d_out, 1, len, call.st);
     if (int rc = call.check("k_unfilter")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
