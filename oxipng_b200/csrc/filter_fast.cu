@@ -423,11 +423,20 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
         r[i][3] = __vsub4(x, __vhaddu4(l, u));
         r[i][4] = __vsub4(x, paeth4(l, u, ul));
 #pragma unroll
-        for (int f = 0; f < 5; f++) {
-            uint32_t p = __shfl_up_sync(0xffffffffu, r[i][f] >> 24, 1);
-            if ((threadIdx.x & 31) == 0)
-                p = k == 0 ? (uint32_t)f : (k < nwords ? residual_at(f, cur, up, 4 * kk - 1, bpp) : 0u);
-            pv[i][f] = p;
+        for (int f = 0; f < 5; f++) pv[i][f] = __shfl_up_sync(0xffffffffu, r[i][f] >> 24, 1);
+        if ((threadIdx.x & 31) == 0) { // lane 0 has no neighbour: the filter id in front of word 0, else one scalar pixel
+            if (k == 0) {
+#pragma unroll
+                for (int f = 0; f < 5; f++) pv[i][f] = (uint32_t)f;
+            } else if (k < nwords) {
+                const int q = 4 * kk - 1;
+                const uint32_t cx = cur[q], cl = cur[q - bpp], cu = up[q], cul = up[q - bpp];
+                pv[i][0] = cx;
+                pv[i][1] = (cx - cl) & 255u;
+                pv[i][2] = (cx - cu) & 255u;
+                pv[i][3] = (cx - ((cl + cu) >> 1)) & 255u;
+                pv[i][4] = (cx - paeth(cl, cu, cul)) & 255u;
+            }
         }
         const int valid = (int)len - 4 * kk;
         // trial 0 (None = the raw bytes, rarely near zero): straight to the big table, this thread owns what it adds first
@@ -446,28 +455,48 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
         }
 #pragma unroll
         for (int f = 1; f < 5; f++) {
+            // Byte-SIMD form of the four windows of this word: t = range codes of its bytes, tpw = codes of the bytes
+            // just before them; a window is in range when neither code has a bit above the low five.
             const uint32_t t = range_code4(r[i][f]);
-            uint32_t tp = (pv[i][f] + 16u) & 255u; // code/flags of the byte before the word
-            uint32_t *tab = sm.small + (f * SMALL_REP + (threadIdx.x & (SMALL_REP - 1))) * SMALL_WORDS;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t tj = (t >> (8 * j)) & 255u;
-                if (j < valid) {
-                    if (((tp | tj) & 0xE0u) == 0) {
-                        const uint32_t idx = (tp << 5) | tj;
-                        atomicAdd(&tab[small_word(idx)], (idx & 1u) ? 0x10000u : 1u);
-                    } else {
-                        om[f] |= 1u << (4 * i + j);
-                        // claim a slot in the trial's short outlier list (the count keeps growing past the list size)
-                        // (once the count has passed the list size nobody needs to add any more: "many" is enough)
-                        if (*(volatile uint32_t *)&sm.s_out_()[f] <= (uint32_t)OUT_LIST) {
-                            const uint32_t slot = atomicAdd(&sm.s_out_()[f], 1u);
-                            if (slot < (uint32_t)OUT_LIST)
-                                sm.s_list[f * OUT_LIST + slot] = (uint16_t)((((tp + 240u) & 255u) << 8) | ((tj + 240u) & 255u));
+            const uint32_t tpw = __byte_perm(t, (pv[i][f] + 16u) & 255u, 0x2104);
+            const uint32_t fl = (t | tpw) & 0xE0E0E0E0u;
+            // replica by lane; each replica is additionally rotated by 8 banks (its base is a multiple of 32 words, so
+            // without the rotation the four replicas of one counter would share a bank)
+            const uint32_t rp = threadIdx.x & (SMALL_REP - 1), rot = rp << 3;
+            uint32_t *tab = sm.small + (f * SMALL_REP + rp) * SMALL_WORDS;
+            if (valid >= 4 && fl == 0) { // the common case: all four windows in range -> no per-window branches
+                // table index first*32 + second for windows 0,2 (16-bit lanes of e) and 1,3 (lanes of o)
+                const uint32_t e = (tpw & 0x00FF00FFu) * 32u + (t & 0x00FF00FFu);
+                const uint32_t o = ((tpw >> 8) & 0x00FF00FFu) * 32u + ((t >> 8) & 0x00FF00FFu);
+                // small_word() ^ rot on both lanes at once: (idx >> 1) ^ ((idx >> 5) & 15) ^ rot
+                const uint32_t rot2 = rot * 0x00010001u;
+                const uint32_t we = ((e >> 1) & 0x01FF01FFu) ^ ((e >> 5) & 0x000F000Fu) ^ rot2;
+                const uint32_t wo = ((o >> 1) & 0x01FF01FFu) ^ ((o >> 5) & 0x000F000Fu) ^ rot2;
+                atomicAdd(&tab[we & 0xFFFFu], 1u + (e & 1u) * 0xFFFFu);
+                atomicAdd(&tab[wo & 0xFFFFu], 1u + (o & 1u) * 0xFFFFu);
+                atomicAdd(&tab[we >> 16], 1u + ((e >> 16) & 1u) * 0xFFFFu);
+                atomicAdd(&tab[wo >> 16], 1u + ((o >> 16) & 1u) * 0xFFFFu);
+            } else {
+                uint32_t tp = tpw & 255u;
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t tj = (t >> (8 * j)) & 255u;
+                    if (j < valid) {
+                        if (((tp | tj) & 0xE0u) == 0) {
+                            const uint32_t idx = (tp << 5) | tj;
+                            atomicAdd(&tab[small_word(idx) ^ rot], (idx & 1u) ? 0x10000u : 1u);
+                        } else {
+                            om[f] |= 1u << (4 * i + j);
+                            // claim a slot in the trial's short outlier list (once the count has passed the list size
+                            // nobody needs to add any more: "many" is enough)
+                            if (*(volatile uint32_t *)&sm.s_out_()[f] <= (uint32_t)OUT_LIST) {
+                                const uint32_t slot = atomicAdd(&sm.s_out_()[f], 1u);
+                                if (slot < (uint32_t)OUT_LIST)
+                                    sm.s_list[f * OUT_LIST + slot] = (uint16_t)((((tp + 240u) & 255u) << 8) | ((tj + 240u) & 255u));
+                            }
                         }
                     }
+                    tp = tj;
                 }
-                tp = tj;
             }
         }
     }
@@ -528,13 +557,13 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
     // sweep the dense tables of trials 1..4 (sum of the replicas; clears what it finds)
     for (uint32_t q = SMALL_WORDS + threadIdx.x; q < 5 * SMALL_WORDS; q += NT) {
         const uint32_t f = q / SMALL_WORDS, w = q % SMALL_WORDS;
-        uint32_t *t = sm.small + f * SMALL_REP * SMALL_WORDS + w;
         uint32_t c0 = 0, c1 = 0;
 #pragma unroll
         for (int rp = 0; rp < SMALL_REP; rp++) {
-            const uint32_t v = t[rp * SMALL_WORDS];
+            uint32_t *cell = sm.small + (f * SMALL_REP + rp) * SMALL_WORDS + (w ^ (uint32_t)(rp << 3));
+            const uint32_t v = *cell;
             if (v) {
-                t[rp * SMALL_WORDS] = 0;
+                *cell = 0;
                 c0 += v & 0xFFFFu;
                 c1 += v >> 16;
             }
