@@ -828,6 +828,10 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_BIGRAM) ? 1 : (SC ==
 
             for (int j2 = 0; j2 < P.set.k; j2++) {
                 const DevStrategy &st = P.set.s[j2];
+                // the write pass of strategy j2 runs on the warps starting at `rot`; the others have nothing to do for
+                // it (a row has (len+16)/16 granules plus <= 31 edge bytes) and skip the decision as well
+                const int rot = (int)((j2 * ((((len + 16) >> 4) + 31) & ~31u)) & (NT - 1));
+                if ((int)(((int)threadIdx.x - rot) & (NT - 1)) >= (int)((((len + 16) >> 4) + 31) & ~31u) + 32) continue;
                 int f = 0;
                 if (st.kind == OXI_BASIC) {
                     f = st.basic;
@@ -859,9 +863,8 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_BIGRAM) ? 1 : (SC ==
                         }
                     }
                 }
-                write_row<NT>(f, cur, up, len, bpp, st.out + img * P.g.out_len + in_off + r,
-                              (int)((j2 * ((((len + 16) >> 4) + 31) & ~31u)) & (NT - 1)));
-                if (tid == 0) st.filters_used[img * P.g.total_rows + r] = (uint8_t)f;
+                write_row<NT>(f, cur, up, len, bpp, st.out + img * P.g.out_len + in_off + r, rot);
+                if (tid == rot) st.filters_used[img * P.g.total_rows + r] = (uint8_t)f;
             }
             if (row_end_barrier) __syncthreads(); // slot `sp` may be refilled by the next iteration's prefetch
         }
