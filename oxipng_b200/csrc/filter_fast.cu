@@ -554,22 +554,27 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             }
         }
     }
-    // sweep the dense tables of trials 1..4 (sum of the replicas; clears what it finds)
-    for (uint32_t q = SMALL_WORDS + threadIdx.x; q < 5 * SMALL_WORDS; q += NT) {
-        const uint32_t f = q / SMALL_WORDS, w = q % SMALL_WORDS;
-        uint32_t c0 = 0, c1 = 0;
+    // sweep the dense tables of trials 1..4 (sum of the replicas; clears what it finds): a quarter of the CTA per trial
+    {
+        constexpr int TPT = NT / 4; // threads per trial
+        const uint32_t f = 1 + threadIdx.x / TPT;
+        uint32_t d = 0, e = 0;
+        for (uint32_t w = threadIdx.x % TPT; w < SMALL_WORDS; w += TPT) {
+            uint32_t c0 = 0, c1 = 0;
 #pragma unroll
-        for (int rp = 0; rp < SMALL_REP; rp++) {
-            uint32_t *cell = sm.small + (f * SMALL_REP + rp) * SMALL_WORDS + (w ^ (uint32_t)(rp << 3));
-            const uint32_t v = *cell;
-            if (v) {
-                *cell = 0;
-                c0 += v & 0xFFFFu;
-                c1 += v >> 16;
+            for (int rp = 0; rp < SMALL_REP; rp++) {
+                uint32_t *cell = sm.small + (f * SMALL_REP + rp) * SMALL_WORDS + (w ^ (uint32_t)(rp << 3));
+                const uint32_t v = *cell;
+                if (v) {
+                    *cell = 0;
+                    c0 += v & 0xFFFFu;
+                    c1 += v >> 16;
+                }
             }
+            d += (c0 != 0) + (c1 != 0);
+            e += (c0 ? ilog2i(c0) : 0u) + (c1 ? ilog2i(c1) : 0u);
         }
-        uint32_t d = (c0 != 0) + (c1 != 0), e = (c0 ? ilog2i(c0) : 0u) + (c1 ? ilog2i(c1) : 0u);
-        // all 32 lanes of a warp sweep the same trial (SMALL_WORDS is a multiple of 32)
+        // all 32 lanes of a warp sweep the same trial (TPT is a multiple of 32)
         d = warp_sum(d);
         e = warp_sum(e);
         if ((threadIdx.x & 31) == 0 && d) {
