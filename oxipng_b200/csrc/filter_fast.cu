@@ -206,11 +206,12 @@ __host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, bool small_tab, uin
 
 // MinSum for all five filters in one sweep. Accumulates S_f = sum over bytes of ||cur-pred_f| - 128|; the caller turns
 // it into the reference's score 128*bytes - S_f + f (the filter-type byte f counts |f| = f, png/mod.rs:409-414).
+// Returns the OR of this thread's row words (for the all-zero-row test, so that no separate scan is needed).
 template <int D, int NT>
-__device__ __forceinline__ void minsum_pass(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
-                                            uint32_t *s_min) {
+__device__ __forceinline__ uint32_t minsum_pass(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
+                                                uint32_t *s_min) {
     const uint32_t nchunks = (len + 15) >> 4;
-    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, nz = 0;
     const uint32_t H = 0x80808080u;
     for (uint32_t c = threadIdx.x; c < nchunks; c += NT) {
         const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
@@ -222,6 +223,7 @@ __device__ __forceinline__ void minsum_pass(const uint8_t *cur, const uint8_t *u
                 const uint32_t m = tail_mask(valid - 4 * k);
                 x &= m; u &= m; l &= m; ul &= m;
             }
+            nz |= x;
             a0 = __vsadu4(x, H) + a0;
             a1 = __vsadu4(__vabsdiffu4(x, l), H) + a1;
             a2 = __vsadu4(__vabsdiffu4(x, u), H) + a2;
@@ -234,6 +236,7 @@ __device__ __forceinline__ void minsum_pass(const uint8_t *cur, const uint8_t *u
         atomicAdd(&s_min[0], a0); atomicAdd(&s_min[1], a1); atomicAdd(&s_min[2], a2);
         atomicAdd(&s_min[3], a3); atomicAdd(&s_min[4], a4);
     }
+    return nz;
 }
 
 __device__ __forceinline__ void hist_add4(uint32_t *h, uint32_t r, int nvalid) {
@@ -799,7 +802,8 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_BIGRAM) ? 1 : (SC ==
             sr.sc = sm.sc + (row_ctr % 3u) * SCORE_WORDS;
             if (SC != 0 && any_heur) {
                 if (tid < (int)SCORE_WORDS) sm.sc[((row_ctr + 1u) % 3u) * SCORE_WORDS + tid] = 0;
-                if (SC & SC_MINSUM) minsum_pass<D, NT>(cur, up, len, shift, sr.s_min_());
+                uint32_t nz = 0;
+                if (SC & SC_MINSUM) nz = minsum_pass<D, NT>(cur, up, len, shift, sr.s_min_());
                 if (SC & SC_ENTROPY) {
                     entropy_pass<D, NT>(cur, up, len, shift, sm.hist);
                     __syncthreads();
@@ -815,9 +819,9 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_BIGRAM) ? 1 : (SC ==
                     else bigram_row<D, NT, 8>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
                 }
                 // all-zero rows short-circuit to None (png/mod.rs:398-404); decided at the scorers' last barrier
-                uint32_t nz = 0;
+                // (the MinSum sweep has already OR-ed the row)
                 const uint4 *c4 = reinterpret_cast<const uint4 *>(cur);
-                const uint32_t nchunks = (len + 15) >> 4;
+                const uint32_t nchunks = (SC & SC_MINSUM) ? 0u : (len + 15) >> 4;
                 for (uint32_t c = tid; c < nchunks; c += NT) {
                     uint4 v = c4[c];
                     const int valid = (int)len - (int)(16 * c);
