@@ -88,11 +88,7 @@ __device__ __forceinline__ uint32_t residual_byte(int f, uint32_t cur, uint32_t 
     return (cur - pred) & 0xFFu;
 }
 
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); } // REDUX.SUM
 __device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -31,7 +31,8 @@ constexpr int HIST_REP = 4;      // copies of each Entropy histogram (lane & 3) 
 constexpr uint32_t PAD = 32;     // zero bytes in front of every staged row (left/upleft of the first pixel)
 constexpr uint32_t SMEM_HDR = 1536;
 constexpr uint32_t SCORE_WORDS = 40;   // s_min/s_ent/s_bgc/s_bge/s_out, 8 words each; three sets rotate row by row
-constexpr int OUT_LIST = 64;         // outlier bigrams per trial that are resolved by one warp instead of the big table
+constexpr uint32_t HSLOTS = 512;     // slots of a trial's outlier hash table (key << 16 | count)
+constexpr int HPROBE = 8;            // probes before an insert gives up and sends the trial's outliers to the big table
 constexpr uint32_t SMEM_LIMIT = 232448; // 227 KB
 
 struct FastParams {
@@ -172,12 +173,12 @@ struct Smem {
     __device__ __forceinline__ uint32_t *s_ent_() const { return sc + 8; }  // [5]
     __device__ __forceinline__ uint32_t *s_bgc_() const { return sc + 16; } // [5] distinct bigrams
     __device__ __forceinline__ uint32_t *s_bge_() const { return sc + 24; } // [5] bigram entropy
-    __device__ __forceinline__ uint32_t *s_out_() const { return sc + 32; } // [5] outlier windows per trial
+    __device__ __forceinline__ uint32_t *s_out_() const { return sc + 32; } // [5] trial flagged: its outliers overflowed the hash table
     uint8_t *rows;     // 3 slots of rb bytes
     uint32_t *hist;    // [5][HIST_REP][256]
     uint32_t *table;   // 32768 words = 65536 u16 counters
     uint32_t *small;   // [5][SMALL_REP][512] words: 32x32 u16 counter tables (in-range bigrams), optional
-    uint16_t *s_list;  // [5][OUT_LIST] outlier bigrams of trials with few of them
+    uint32_t *ohash;   // [4][HSLOTS] outlier bigrams of trials 1..4: open-addressing tables of (key << 16 | count)
 };
 template <int SC>
 __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot) {
@@ -185,16 +186,16 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot
     s.bar = reinterpret_cast<uint64_t *>(base);
     uint32_t *u = reinterpret_cast<uint32_t *>(base + 64);
     s.sc = u; // set 0; sets 1 and 2 follow at SCORE_WORDS strides
-    s.s_list = reinterpret_cast<uint16_t *>(base + 768);
     s.rows = base + SMEM_HDR;
     uint8_t *p = s.rows + nslot * (size_t)rb;
     s.hist = reinterpret_cast<uint32_t *>(p);
     if (SC & SC_ENTROPY) p += 5 * HIST_REP * 256 * 4;
     s.table = reinterpret_cast<uint32_t *>(p);
     s.small = reinterpret_cast<uint32_t *>(p + 65536 * 2);
+    s.ohash = s.small + 5 * SMALL_REP * SMALL_WORDS;
     return s;
 }
-constexpr uint32_t SMALL_BYTES = 5 * SMALL_REP * SMALL_WORDS * 4;
+constexpr uint32_t SMALL_BYTES = 5 * SMALL_REP * SMALL_WORDS * 4 + 4 * HSLOTS * 4; // dense tables + outlier hashes
 __host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, bool small_tab, uint32_t nslot = 3) {
     uint32_t b = SMEM_HDR + nslot * rb;
     if (sc & SC_ENTROPY) b += 5 * HIST_REP * 256 * 4;
@@ -393,9 +394,29 @@ __device__ __forceinline__ void bigram_row(const uint8_t *cur, const uint8_t *up
 // private to its trial and to the lane's replica (lane & 3), trials 1..4 in one phase; a sweep over the 4 x 4 x 1024
 // counters then yields distinct count and entropy with no ownership bookkeeping.  Trial 0 (None: the raw bytes) is
 // almost never near zero, so it goes straight to the 65536-entry table in the same phase (returning adds, the first
-// adder owns the bigram) and its owners read/clear the counts while the other trials are being swept.  The remaining (outlier) windows take the big-table / owner path, trial by trial, and
-// only for trials that have any.  Exact for any data: every window is counted in exactly one of the two tables, and
-// the two key sets are disjoint.
+// adder owns the bigram) and its owners read/clear the counts while the other trials are being swept.  The remaining
+// (outlier) windows of a trial go to a small open-addressing hash table of (key, count) that is swept together with the
+// dense tables; a trial whose outliers crowd its hash table in some row takes the big-table / owner path for them instead, trial
+// by trial.  Exact for any data: every window is counted in exactly one structure, and their key sets are disjoint.
+// Outlier keys are never 0 (one of the two bytes lies outside [-16, 15]), so an empty slot is 0; a count is at most the
+// number of windows of a row (<= 8192), so it cannot reach the key bits.  Returns false when no slot was found within
+// HPROBE probes (table crowded): the caller then flags the trial for the big-table path.
+__device__ __forceinline__ bool ohash_add(uint32_t *h, uint32_t key) {
+    uint32_t s = ((key * 40503u) >> 7) & (HSLOTS - 1);
+    for (int probe = 0; probe < HPROBE; probe++) {
+        uint32_t cur = *(volatile uint32_t *)&h[s];
+        if (cur == 0) {
+            cur = atomicCAS(&h[s], 0u, (key << 16) | 1u);
+            if (cur == 0) return true;
+        }
+        if ((cur >> 16) == key) {
+            atomicAdd(&h[s], 1u);
+            return true;
+        }
+        s = (s + 1) & (HSLOTS - 1);
+    }
+    return false;
+}
 __device__ __forceinline__ uint32_t range_code4(uint32_t r) { // per byte: (b + 16) mod 256 (no carries across bytes)
     return ((r & 0x7F7F7F7Fu) + 0x10101010u) ^ (r & 0x80808080u);
 }
@@ -489,12 +510,11 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
                             atomicAdd(&tab[small_word(idx) ^ rot], (idx & 1u) ? 0x10000u : 1u);
                         } else {
                             om[f] |= 1u << (4 * i + j);
-                            // claim a slot in the trial's short outlier list (once the count has passed the list size
-                            // nobody needs to add any more: "many" is enough)
-                            if (*(volatile uint32_t *)&sm.s_out_()[f] <= (uint32_t)OUT_LIST) {
-                                const uint32_t slot = atomicAdd(&sm.s_out_()[f], 1u);
-                                if (slot < (uint32_t)OUT_LIST)
-                                    sm.s_list[f * OUT_LIST + slot] = (uint16_t)((((tp + 240u) & 255u) << 8) | ((tj + 240u) & 255u));
+                            // outliers go to the trial's hash table until an insert finds it crowded; from then on
+                            // the trial is flagged and all its outliers take the big-table path after the barrier
+                            if (*(volatile uint32_t *)&sm.s_out_()[f] == 0) {
+                                if (!ohash_add(sm.ohash + (f - 1) * HSLOTS, (((tp + 240u) & 255u) << 8) | ((tj + 240u) & 255u)))
+                                    *(volatile uint32_t *)&sm.s_out_()[f] = 1u;
                             }
                         }
                     }
@@ -532,31 +552,6 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             atomicAdd(&sm.s_bge_()[0], ent);
         }
     }
-    // trials with only a few outliers: warp f dedupes the list of trial f by brute force (no table, no barrier)
-    if ((threadIdx.x >> 5) >= 1 && (threadIdx.x >> 5) < 5) {
-        const int f = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const uint32_t n = sm.s_out_()[f];
-        if (n > 0 && n <= (uint32_t)OUT_LIST) {
-            uint32_t dis = 0, ent = 0;
-            for (uint32_t e = lane; e < n; e += 32) {
-                const uint16_t me = sm.s_list[f * OUT_LIST + e];
-                uint32_t cnt = 0;
-                bool first = true;
-                for (uint32_t q = 0; q < n; q++) {
-                    const bool eq = sm.s_list[f * OUT_LIST + q] == me;
-                    cnt += eq;
-                    first &= !(eq && q < e);
-                }
-                if (first) { dis++; ent += ilog2i(cnt); }
-            }
-            dis = warp_sum(dis);
-            ent = warp_sum(ent);
-            if (lane == 0) {
-                atomicAdd(&sm.s_bgc_()[f], dis);
-                atomicAdd(&sm.s_bge_()[f], ent);
-            }
-        }
-    }
     // sweep the dense tables of trials 1..4 (sum of the replicas; clears what it finds): a quarter of the CTA per trial
     {
         constexpr int TPT = NT / 4; // threads per trial
@@ -577,6 +572,19 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             d += (c0 != 0) + (c1 != 0);
             e += (c0 ? ilog2i(c0) : 0u) + (c1 ? ilog2i(c1) : 0u);
         }
+        // the trial's outlier hash table: counted unless the trial overflowed it (then only cleared)
+        const bool hashed = sm.s_out_()[f] == 0;
+        for (uint32_t w = threadIdx.x % TPT; w < HSLOTS; w += TPT) {
+            uint32_t *cell = sm.ohash + (f - 1) * HSLOTS + w;
+            const uint32_t v = *cell;
+            if (v) {
+                *cell = 0;
+                if (hashed) {
+                    d += 1;
+                    e += ilog2i(v & 0xFFFFu);
+                }
+            }
+        }
         // all 32 lanes of a warp sweep the same trial (TPT is a multiple of 32)
         d = warp_sum(d);
         e = warp_sum(e);
@@ -586,12 +594,11 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
         }
     }
     // trials 1..4 with many outliers: big table + owner pass, one trial at a time (after trial 0 has cleaned up)
-    const bool any_heavy = sm.s_out_()[1] > (uint32_t)OUT_LIST || sm.s_out_()[2] > (uint32_t)OUT_LIST ||
-                           sm.s_out_()[3] > (uint32_t)OUT_LIST || sm.s_out_()[4] > (uint32_t)OUT_LIST; // uniform
+    const bool any_heavy = (sm.s_out_()[1] | sm.s_out_()[2] | sm.s_out_()[3] | sm.s_out_()[4]) != 0; // uniform
     if (any_heavy) __syncthreads();
 #pragma unroll
     for (int f = 1; f < 5; f++) {
-        if (sm.s_out_()[f] <= (uint32_t)OUT_LIST) continue; // uniform: final before the first barrier above
+        if (sm.s_out_()[f] == 0) continue; // uniform: final before the first barrier above
         uint32_t own = 0;
 #pragma unroll
         for (int i = 0; i < WPT; i++) {
@@ -773,8 +780,8 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_BIGRAM) ? 1 : (SC ==
         }
         __syncthreads();
 
+        uint32_t sp = 0, sc_ = 1, sn = 2; // ring slots of the previous, current and next row
         for (uint32_t k = k0; k < k1; k++) {
-            const uint32_t j = k - k0 + 1, sc_ = j % NS, sp = (j + NS - 1) % NS, sn = (j + 1) % NS;
             const uint8_t *cur = sm.rows + sc_ * (size_t)P.rb + PAD;
             const uint8_t *up = sm.rows + sp * (size_t)P.rb + PAD;
             if (k + 1 < k1) { // stream the next row in behind the current one
@@ -876,6 +883,9 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_BIGRAM) ? 1 : (SC ==
                 if (tid == rot) st.filters_used[img * P.g.total_rows + r] = (uint8_t)f;
             }
             if (row_end_barrier) __syncthreads(); // slot `sp` may be refilled by the next iteration's prefetch
+            sp = sc_;
+            sc_ = sn;
+            sn = sn + 1 == NS ? 0 : sn + 1;
         }
         if (!row_end_barrier) __syncthreads(); // the next band's prologue rewrites slots 0 and 1
     }

@@ -158,6 +158,27 @@ def test_fast_tier_covers_benchmark_shapes():
         _check(ih, d, alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["None", "Bigrams", "BigEnt"], label="o4")
 
 
+def test_bigram_outlier_paths():
+    """Bigram scorers on smooth images with a controlled number of spikes per row: few outlier windows (hash-table
+    path), around the hash capacity, and far beyond it (big-table path), plus hot spikes (one value repeated) that
+    stress the hash counters; 1-word and 2-words-per-thread row lengths."""
+    import oxipng_b200 as ox
+    rng = np.random.default_rng(77)
+    for (w, h) in [(1024, 12), (2000, 10), (300, 9)]:
+        for spikes in (0, 3, 40, 110, 128, 135, 300, 1500):
+            for hot in (False, True):
+                ih, d = helpers.synth_image(w, h, 6, 8, 900 + spikes, "photo")
+                a = np.frombuffer(bytes(d), dtype=np.uint8).copy().reshape(h, -1)
+                for y in range(h):
+                    n = min(spikes, a.shape[1])
+                    pos = rng.choice(a.shape[1], size=n, replace=False)
+                    a[y, pos] = 200 if hot else rng.integers(0, 256, size=n, dtype=np.uint8)
+                _check(ih, a.tobytes(), alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["Bigrams", "BigEnt"],
+                       label=f"spikes/{w}x{h}/{spikes}/{hot}")
+                _check(ih, a.tobytes(), alphas=(False,), flags=ox.FLAG_FORCE_FAST,
+                       strategies=["None", "Bigrams", "BigEnt"], label=f"spikes-o4/{w}x{h}/{spikes}/{hot}")
+
+
 def test_fast_tier_batch_many_images():
     import oxipng_b200 as ox
     n = 37
