@@ -27,6 +27,7 @@ namespace oxi {
 namespace {
 
 constexpr int SC_MINSUM = 1, SC_ENTROPY = 2, SC_BIGRAM = 4;
+constexpr int SC_HALF = 8; // with SC_BIGRAM alone, rows <= 4096 bytes: 512-thread CTAs, two resident per SM
 constexpr int HIST_REP = 4;      // copies of each Entropy histogram (lane & 3) to thin same-address atomics
 constexpr uint32_t PAD = 32;     // zero bytes in front of every staged row (left/upleft of the first pixel)
 constexpr uint32_t SMEM_HDR = 1536;
@@ -45,10 +46,11 @@ struct FastParams {
     uint32_t rb;    // bytes of one ring slot
     uint32_t shift; // 8 * (bpp % 4): funnel-shift amount that turns a row word into its "left" word
     uint32_t nslot;     // ring slots (4 when shared memory allows: removes the end-of-row barrier; else 3)
+    uint32_t h0_slots;  // bigram scorer with small_tab: slots of the trial-0 hash table (power of two, > 2 * row bytes)
     uint32_t small_tab; // bigram scorer: five dense 64x64 in-range tables are carved (rows <= 8192 bytes)
 };
 
-__host__ __device__ constexpr int threads_for(int sc) { return (sc & SC_BIGRAM) ? 1024 : 256; }
+__host__ __device__ constexpr int threads_for(int sc) { return (sc & SC_HALF) ? 512 : (sc & SC_BIGRAM) ? 1024 : 256; }
 
 // ---- PTX wrappers: mbarrier + 1-D bulk tensor-memory-accelerator copy -----------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -176,12 +178,12 @@ struct Smem {
     __device__ __forceinline__ uint32_t *s_out_() const { return sc + 32; } // [5] trial flagged: its outliers overflowed the hash table
     uint8_t *rows;     // 3 slots of rb bytes
     uint32_t *hist;    // [5][HIST_REP][256]
-    uint32_t *table;   // 32768 words = 65536 u16 counters
-    uint32_t *small;   // [5][SMALL_REP][512] words: 32x32 u16 counter tables (in-range bigrams), optional
+    uint32_t *table;   // 32768 words = 65536 u16 counters, or (small_tab) the h0_slots-word hash table of whole rows
+    uint32_t *small;   // [4][SMALL_REP][512] words: 32x32 u16 counter tables (in-range bigrams of trials 1..4), optional
     uint32_t *ohash;   // [4][HSLOTS] outlier bigrams of trials 1..4: open-addressing tables of (key << 16 | count)
 };
 template <int SC>
-__device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot) {
+__device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot, uint32_t table_words) {
     Smem s;
     s.bar = reinterpret_cast<uint64_t *>(base);
     uint32_t *u = reinterpret_cast<uint32_t *>(base + 64);
@@ -191,15 +193,16 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot
     s.hist = reinterpret_cast<uint32_t *>(p);
     if (SC & SC_ENTROPY) p += 5 * HIST_REP * 256 * 4;
     s.table = reinterpret_cast<uint32_t *>(p);
-    s.small = reinterpret_cast<uint32_t *>(p + 65536 * 2);
-    s.ohash = s.small + 5 * SMALL_REP * SMALL_WORDS;
+    s.small = s.table + table_words;
+    s.ohash = s.small + 4 * SMALL_REP * SMALL_WORDS;
     return s;
 }
-constexpr uint32_t SMALL_BYTES = 5 * SMALL_REP * SMALL_WORDS * 4 + 4 * HSLOTS * 4; // dense tables + outlier hashes
-__host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, bool small_tab, uint32_t nslot = 3) {
+constexpr uint32_t SMALL_BYTES = 4 * SMALL_REP * SMALL_WORDS * 4 + 4 * HSLOTS * 4; // dense tables + outlier hashes
+// h0_slots != 0: the small-table layout (hash of whole rows + dense tables + outlier hashes); 0: the 65536-entry table
+__host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, uint32_t h0_slots, uint32_t nslot = 3) {
     uint32_t b = SMEM_HDR + nslot * rb;
     if (sc & SC_ENTROPY) b += 5 * HIST_REP * 256 * 4;
-    if (sc & SC_BIGRAM) b += 65536 * 2 + (small_tab ? SMALL_BYTES : 0);
+    if (sc & SC_BIGRAM) b += h0_slots ? h0_slots * 4 + SMALL_BYTES : 65536 * 2;
     return b;
 }
 
@@ -388,19 +391,59 @@ __device__ __forceinline__ void bigram_row(const uint8_t *cur, const uint8_t *up
 }
 
 // ---- Bigrams/BigEnt, all five trials at once (rows <= 8192 bytes) ---------------------------------------------------
-// Filtered rows of natural images are sharply peaked around 0, which makes returning atomics on one shared table
-// serialise (ncu: 10-32 wavefronts per ATOMS; same-address lanes serialise with or without a return value).  Here a
-// window whose two stream bytes both lie in [-16, 15] (as i8) is counted in a dense, bank-swizzled 32x32 u16 table
-// private to its trial and to the lane's replica (lane & 3), trials 1..4 in one phase; a sweep over the 4 x 4 x 1024
-// counters then yields distinct count and entropy with no ownership bookkeeping.  Trial 0 (None: the raw bytes) is
-// almost never near zero, so it goes straight to the 65536-entry table in the same phase (returning adds, the first
-// adder owns the bigram) and its owners read/clear the counts while the other trials are being swept.  The remaining
-// (outlier) windows of a trial go to a small open-addressing hash table of (key, count) that is swept together with the
-// dense tables; a trial whose outliers crowd its hash table in some row takes the big-table / owner path for them instead, trial
-// by trial.  Exact for any data: every window is counted in exactly one structure, and their key sets are disjoint.
-// Outlier keys are never 0 (one of the two bytes lies outside [-16, 15]), so an empty slot is 0; a count is at most the
-// number of windows of a row (<= 8192), so it cannot reach the key bits.  Returns false when no slot was found within
-// HPROBE probes (table crowded): the caller then flags the trial for the big-table path.
+// Filtered rows of natural images are sharply peaked around 0, which makes atomics on one shared table serialise
+// (ncu: 10-32 wavefronts per ATOMS; same-address lanes serialise with or without a return value), and a directly
+// indexed table of all 65536 bigrams (128 KB) limits the SM to one CTA.  Instead, per row:
+//  * trials 1..4: a window whose two stream bytes both lie in [-16, 15] (as i8) is counted in a dense, bank-swizzled
+//    32x32 u16 table private to its trial and to the lane's replica (lane & 3); the remaining (outlier) windows go to a
+//    small open-addressing hash table of (key, count) per trial;
+//  * trial 0 (None: the raw bytes, rarely near zero) goes to one hash table `h0` with more than twice as many slots as
+//    the row has windows, so an insert always finds a slot;
+//  * after one barrier every table is swept (and cleared): non-zero counters are the distinct bigrams, their counts
+//    give the entropy.  No ownership bookkeeping, nothing kept in registers across the barrier;
+//  * a trial whose outliers crowd its small hash in some row (noise-like data) is flagged; its outliers are then
+//    re-derived from the staged row and counted in h0, trial by trial, after h0 has been swept.
+// Exact for any data: every window is counted in exactly one structure, and their key sets are disjoint.
+
+// h0 entries are ((key + 1) << 14) | count: key + 1 is never 0, and a count is at most 8192 (row bytes).
+__device__ __forceinline__ void h0_collide(uint32_t *h, uint32_t s, uint32_t tag, uint32_t old, uint32_t mask) {
+    for (;;) {
+        if ((old & ~0x3FFFu) == tag) {
+            atomicAdd(&h[s], 1u);
+            return;
+        }
+        s = (s + 1) & mask;
+        old = atomicCAS(&h[s], 0u, tag | 1u);
+        if (old == 0) return;
+    }
+}
+__device__ __forceinline__ uint32_t h0_slot(uint32_t key, uint32_t hshift) { return (key * 0x9E3779B1u) >> hshift; }
+__device__ __forceinline__ void h0_add(uint32_t *h, uint32_t key, uint32_t hshift, uint32_t mask) {
+    const uint32_t tag = (key + 1u) << 14, s = h0_slot(key, hshift);
+    const uint32_t old = atomicCAS(&h[s], 0u, tag | 1u);
+    if (old != 0) h0_collide(h, s, tag, old, mask);
+}
+// sweep (and clear) h0: distinct keys and sum of ilog2i(count) over this thread's slots
+template <int NT>
+__device__ __forceinline__ void h0_sweep(uint32_t *h, uint32_t slots, uint32_t &d, uint32_t &e) {
+    uint4 *h4 = reinterpret_cast<uint4 *>(h);
+    for (uint32_t q = threadIdx.x; q < slots / 4; q += NT) {
+        const uint4 v = h4[q];
+        if (v.x | v.y | v.z | v.w) {
+            h4[q] = make_uint4(0, 0, 0, 0);
+            const uint32_t c0 = v.x & 0x3FFFu, c1 = v.y & 0x3FFFu, c2 = v.z & 0x3FFFu, c3 = v.w & 0x3FFFu;
+            d += (c0 != 0) + (c1 != 0) + (c2 != 0) + (c3 != 0);
+            if (c0 > 1) e += ilog2i(c0);
+            if (c1 > 1) e += ilog2i(c1);
+            if (c2 > 1) e += ilog2i(c2);
+            if (c3 > 1) e += ilog2i(c3);
+        }
+    }
+}
+
+// Outlier keys of trials 1..4 are never 0 (one of the two bytes lies outside [-16, 15]), so an empty slot is 0; a count
+// is at most the number of windows of a row (<= 8192), so it cannot reach the key bits.  Returns false when no slot was
+// found within HPROBE probes (table crowded): the caller then flags the trial.
 __device__ __forceinline__ bool ohash_add(uint32_t *h, uint32_t key) {
     uint32_t s = ((key * 40503u) >> 7) & (HSLOTS - 1);
     for (int probe = 0; probe < HPROBE; probe++) {
@@ -422,12 +465,11 @@ __device__ __forceinline__ uint32_t range_code4(uint32_t r) { // per byte: (b + 
 }
 template <int D, int NT, int WPT>
 __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
-                                                 const Smem &sm) {
+                                                 const Smem &sm, uint32_t h0_slots) {
     const uint32_t nwords = (len + 3) >> 2;
     const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur), *uw = reinterpret_cast<const uint32_t *>(up);
-    uint16_t *t16 = reinterpret_cast<uint16_t *>(sm.table);
-    uint32_t r[WPT][5], pv[WPT][5];
-    uint32_t om[5] = {0, 0, 0, 0, 0}; // trial 0: windows this thread owns in the big table; 1..4: its outlier windows
+    uint32_t *h0 = sm.table;
+    const uint32_t hmask = h0_slots - 1, hshift = (uint32_t)__clz((int)h0_slots) + 1; // 32 - log2(slots)
 #pragma unroll
     for (int i = 0; i < WPT; i++) {
         const uint32_t k = threadIdx.x + i * NT;
@@ -441,53 +483,57 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             ul = D == 2 ? uw[kk - 2] : D == 1 ? __funnelshift_l(uw[kk - 2], uw[kk - 1], shift)
                                               : __funnelshift_l(uw[kk - 1], uw[kk], shift);
         }
-        r[i][0] = x;
-        r[i][1] = __vsub4(x, l);
-        r[i][2] = __vsub4(x, u);
-        r[i][3] = __vsub4(x, __vhaddu4(l, u));
-        r[i][4] = __vsub4(x, paeth4(l, u, ul));
+        uint32_t r[5], pv[5];
+        r[0] = x;
+        r[1] = __vsub4(x, l);
+        r[2] = __vsub4(x, u);
+        r[3] = __vsub4(x, __vhaddu4(l, u));
+        r[4] = __vsub4(x, paeth4(l, u, ul));
 #pragma unroll
-        for (int f = 0; f < 5; f++) pv[i][f] = __shfl_up_sync(0xffffffffu, r[i][f] >> 24, 1);
+        for (int f = 0; f < 5; f++) pv[f] = __shfl_up_sync(0xffffffffu, r[f] >> 24, 1);
         if ((threadIdx.x & 31) == 0) { // lane 0 has no neighbour: the filter id in front of word 0, else one scalar pixel
             if (k == 0) {
 #pragma unroll
-                for (int f = 0; f < 5; f++) pv[i][f] = (uint32_t)f;
+                for (int f = 0; f < 5; f++) pv[f] = (uint32_t)f;
             } else if (k < nwords) {
                 const int q = 4 * kk - 1;
                 const uint32_t cx = cur[q], cl = cur[q - bpp], cu = up[q], cul = up[q - bpp];
-                pv[i][0] = cx;
-                pv[i][1] = (cx - cl) & 255u;
-                pv[i][2] = (cx - cu) & 255u;
-                pv[i][3] = (cx - ((cl + cu) >> 1)) & 255u;
-                pv[i][4] = (cx - paeth(cl, cu, cul)) & 255u;
+                pv[0] = cx;
+                pv[1] = (cx - cl) & 255u;
+                pv[2] = (cx - cu) & 255u;
+                pv[3] = (cx - ((cl + cu) >> 1)) & 255u;
+                pv[4] = (cx - paeth(cl, cu, cul)) & 255u;
             }
         }
         const int valid = (int)len - 4 * kk;
-        // trial 0 (None = the raw bytes, rarely near zero): straight to the big table, this thread owns what it adds first
+        // trial 0: the four windows' claims go out together, collisions / repeats are settled afterwards
         {
-            uint32_t prev = pv[i][0];
+            uint32_t tag[4], slot[4], old[4];
+            // keys (prev << 8 | byte) of windows 0..3: bytes 0..3 of (x << 8 | pv) paired with bytes of x
+            const uint32_t pw = __byte_perm(x, pv[0], 0x2104);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint32_t b = (x >> (8 * j)) & 255u;
-                const uint32_t bg = (prev << 8) | b;
-                prev = b;
-                if (j < valid) {
-                    const uint32_t old = atomicAdd(&sm.table[big_word(bg)], (bg & 1u) ? 0x10000u : 1u);
-                    if (((bg & 1u) ? (old >> 16) : (old & 0xFFFFu)) == 0) om[0] |= 1u << (4 * i + j);
-                }
+                const uint32_t key = (((pw >> (8 * j)) & 255u) << 8) | ((x >> (8 * j)) & 255u);
+                tag[j] = (key + 1u) << 14;
+                slot[j] = h0_slot(key, hshift);
             }
+#pragma unroll
+            for (int j = 0; j < 4; j++) old[j] = j < valid ? atomicCAS(&h0[slot[j]], 0u, tag[j] | 1u) : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (old[j] != 0) h0_collide(h0, slot[j], tag[j], old[j], hmask);
         }
 #pragma unroll
         for (int f = 1; f < 5; f++) {
             // Byte-SIMD form of the four windows of this word: t = range codes of its bytes, tpw = codes of the bytes
             // just before them; a window is in range when neither code has a bit above the low five.
-            const uint32_t t = range_code4(r[i][f]);
-            const uint32_t tpw = __byte_perm(t, (pv[i][f] + 16u) & 255u, 0x2104);
+            const uint32_t t = range_code4(r[f]);
+            const uint32_t tpw = __byte_perm(t, (pv[f] + 16u) & 255u, 0x2104);
             const uint32_t fl = (t | tpw) & 0xE0E0E0E0u;
             // replica by lane; each replica is additionally rotated by 8 banks (its base is a multiple of 32 words, so
             // without the rotation the four replicas of one counter would share a bank)
             const uint32_t rp = threadIdx.x & (SMALL_REP - 1), rot = rp << 3;
-            uint32_t *tab = sm.small + (f * SMALL_REP + rp) * SMALL_WORDS;
+            uint32_t *tab = sm.small + ((f - 1) * SMALL_REP + rp) * SMALL_WORDS;
             if (valid >= 4 && fl == 0) { // the common case: all four windows in range -> no per-window branches
                 // table index first*32 + second for windows 0,2 (16-bit lanes of e) and 1,3 (lanes of o)
                 const uint32_t e = (tpw & 0x00FF00FFu) * 32u + (t & 0x00FF00FFu);
@@ -508,14 +554,11 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
                         if (((tp | tj) & 0xE0u) == 0) {
                             const uint32_t idx = (tp << 5) | tj;
                             atomicAdd(&tab[small_word(idx) ^ rot], (idx & 1u) ? 0x10000u : 1u);
-                        } else {
-                            om[f] |= 1u << (4 * i + j);
-                            // outliers go to the trial's hash table until an insert finds it crowded; from then on
-                            // the trial is flagged and all its outliers take the big-table path after the barrier
-                            if (*(volatile uint32_t *)&sm.s_out_()[f] == 0) {
-                                if (!ohash_add(sm.ohash + (f - 1) * HSLOTS, (((tp + 240u) & 255u) << 8) | ((tj + 240u) & 255u)))
-                                    *(volatile uint32_t *)&sm.s_out_()[f] = 1u;
-                            }
+                        } else if (*(volatile uint32_t *)&sm.s_out_()[f] == 0) {
+                            // outliers go to the trial's hash table until an insert finds it crowded; from then on the
+                            // trial is flagged and all its outliers are counted in h0 after the barrier
+                            if (!ohash_add(sm.ohash + (f - 1) * HSLOTS, (((tp + 240u) & 255u) << 8) | ((tj + 240u) & 255u)))
+                                *(volatile uint32_t *)&sm.s_out_()[f] = 1u;
                         }
                     }
                     tp = tj;
@@ -524,35 +567,18 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
         }
     }
     __syncthreads();
-    // trial 0: owners read the final counts and clear the entries (no other trial is in the big table now)
+    // trial 0: sweep h0
     {
-        uint32_t distinct = 0, ent = 0;
-        if (om[0]) {
-#pragma unroll
-            for (int i = 0; i < WPT; i++) {
-                uint32_t prev = pv[i][0];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t b = (r[i][0] >> (8 * j)) & 255u;
-                    const uint32_t bg = (prev << 8) | b;
-                    prev = b;
-                    if ((om[0] >> (4 * i + j)) & 1u) {
-                        const uint32_t cnt = t16[(big_word(bg) << 1) | (bg & 1u)];
-                        t16[(big_word(bg) << 1) | (bg & 1u)] = 0;
-                        distinct += 1;
-                        ent += ilog2i(cnt);
-                    }
-                }
-            }
-        }
-        distinct = warp_sum(distinct);
-        ent = warp_sum(ent);
-        if ((threadIdx.x & 31) == 0 && distinct) {
-            atomicAdd(&sm.s_bgc_()[0], distinct);
-            atomicAdd(&sm.s_bge_()[0], ent);
+        uint32_t d = 0, e = 0;
+        h0_sweep<NT>(h0, h0_slots, d, e);
+        d = warp_sum(d);
+        e = warp_sum(e);
+        if ((threadIdx.x & 31) == 0 && d) {
+            atomicAdd(&sm.s_bgc_()[0], d);
+            atomicAdd(&sm.s_bge_()[0], e);
         }
     }
-    // sweep the dense tables of trials 1..4 (sum of the replicas; clears what it finds): a quarter of the CTA per trial
+    // trials 1..4: sweep the dense tables (sum of the replicas) and the outlier hash, a quarter of the CTA per trial
     {
         constexpr int TPT = NT / 4; // threads per trial
         const uint32_t f = 1 + threadIdx.x / TPT;
@@ -561,7 +587,7 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             uint32_t c0 = 0, c1 = 0;
 #pragma unroll
             for (int rp = 0; rp < SMALL_REP; rp++) {
-                uint32_t *cell = sm.small + (f * SMALL_REP + rp) * SMALL_WORDS + (w ^ (uint32_t)(rp << 3));
+                uint32_t *cell = sm.small + ((f - 1) * SMALL_REP + rp) * SMALL_WORDS + (w ^ (uint32_t)(rp << 3));
                 const uint32_t v = *cell;
                 if (v) {
                     *cell = 0;
@@ -572,7 +598,7 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             d += (c0 != 0) + (c1 != 0);
             e += (c0 ? ilog2i(c0) : 0u) + (c1 ? ilog2i(c1) : 0u);
         }
-        // the trial's outlier hash table: counted unless the trial overflowed it (then only cleared)
+        // the trial's outlier hash table: counted unless the trial is flagged (then only cleared)
         const bool hashed = sm.s_out_()[f] == 0;
         for (uint32_t w = threadIdx.x % TPT; w < HSLOTS; w += TPT) {
             uint32_t *cell = sm.ohash + (f - 1) * HSLOTS + w;
@@ -593,52 +619,25 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             atomicAdd(&sm.s_bge_()[f], e);
         }
     }
-    // trials 1..4 with many outliers: big table + owner pass, one trial at a time (after trial 0 has cleaned up)
-    const bool any_heavy = (sm.s_out_()[1] | sm.s_out_()[2] | sm.s_out_()[3] | sm.s_out_()[4]) != 0; // uniform
-    if (any_heavy) __syncthreads();
-#pragma unroll
+    // flagged trials: their outlier windows, re-derived from the staged row, are counted in h0, one trial at a time
+    const uint32_t flagged = sm.s_out_()[1] | sm.s_out_()[2] << 1 | sm.s_out_()[3] << 2 | sm.s_out_()[4] << 3; // uniform
+    if (flagged == 0) return;
+    __syncthreads(); // h0 is clean
     for (int f = 1; f < 5; f++) {
-        if (sm.s_out_()[f] == 0) continue; // uniform: final before the first barrier above
-        uint32_t own = 0;
-#pragma unroll
-        for (int i = 0; i < WPT; i++) {
-            uint32_t prev = pv[i][f];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t b = (r[i][f] >> (8 * j)) & 255u;
-                const uint32_t bg = (prev << 8) | b;
-                prev = b;
-                if ((om[f] >> (4 * i + j)) & 1u) {
-                    const uint32_t old = atomicAdd(&sm.table[big_word(bg)], (bg & 1u) ? 0x10000u : 1u);
-                    if (((bg & 1u) ? (old >> 16) : (old & 0xFFFFu)) == 0) own |= 1u << (4 * i + j);
-                }
-            }
+        if (!((flagged >> (f - 1)) & 1u)) continue;
+        for (uint32_t p = threadIdx.x; p < len; p += NT) {
+            const uint32_t b = residual_at(f, cur, up, (int)p, bpp);
+            const uint32_t pr = p ? residual_at(f, cur, up, (int)p - 1, bpp) : (uint32_t)f;
+            if ((((pr + 16u) | (b + 16u)) & 0xE0u) != 0) h0_add(h0, (pr << 8) | b, hshift, hmask);
         }
         __syncthreads();
-        uint32_t distinct = 0, ent = 0;
-        if (own) {
-#pragma unroll
-            for (int i = 0; i < WPT; i++) {
-                uint32_t prev = pv[i][f];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t b = (r[i][f] >> (8 * j)) & 255u;
-                    const uint32_t bg = (prev << 8) | b;
-                    prev = b;
-                    if ((own >> (4 * i + j)) & 1u) {
-                        const uint32_t cnt = t16[(big_word(bg) << 1) | (bg & 1u)];
-                        t16[(big_word(bg) << 1) | (bg & 1u)] = 0;
-                        distinct += 1;
-                        ent += ilog2i(cnt);
-                    }
-                }
-            }
-        }
-        distinct = warp_sum(distinct);
-        ent = warp_sum(ent);
-        if ((threadIdx.x & 31) == 0 && distinct) {
-            atomicAdd(&sm.s_bgc_()[f], distinct);
-            atomicAdd(&sm.s_bge_()[f], ent);
+        uint32_t d = 0, e = 0;
+        h0_sweep<NT>(h0, h0_slots, d, e);
+        d = warp_sum(d);
+        e = warp_sum(e);
+        if ((threadIdx.x & 31) == 0 && d) {
+            atomicAdd(&sm.s_bgc_()[f], d);
+            atomicAdd(&sm.s_bge_()[f], e);
         }
         __syncthreads();
     }
@@ -706,11 +705,11 @@ __device__ __forceinline__ void coop_load_row(uint8_t *dst, const uint8_t *src, 
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 template <int D, int SC>
-__global__ void __launch_bounds__(threads_for(SC), (SC & SC_BIGRAM) ? 1 : (SC == SC_MINSUM || SC == 0) ? 3 : 2) k_fast(const __grid_constant__ FastParams P) {
+__global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC_BIGRAM) ? 1 : (SC == SC_MINSUM || SC == 0) ? 3 : 2) k_fast(const __grid_constant__ FastParams P) {
     constexpr int NT = threads_for(SC);
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t NS = P.nslot;
-    const Smem sm = carve<SC>(smem_raw, P.rb, NS);
+    const Smem sm = carve<SC>(smem_raw, P.rb, NS, P.small_tab ? P.h0_slots : 32768u);
     const int tid = threadIdx.x;
     const int bpp = (int)P.g.bpp;
     const uint32_t shift = P.shift;
@@ -725,7 +724,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_BIGRAM) ? 1 : (SC ==
     if (SC & SC_ENTROPY)
         for (uint32_t i = tid; i < 5 * HIST_REP * 256; i += NT) sm.hist[i] = 0;
     if (SC & SC_BIGRAM) {
-        for (uint32_t i = tid; i < 32768; i += NT) sm.table[i] = 0;
+        for (uint32_t i = tid; i < (P.small_tab ? P.h0_slots : 32768u); i += NT) sm.table[i] = 0;
         if (P.small_tab)
             for (uint32_t i = tid; i < SMALL_BYTES / 4; i += NT) sm.small[i] = 0;
     }
@@ -818,8 +817,8 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_BIGRAM) ? 1 : (SC ==
                 }
                 if (SC & SC_BIGRAM) {
                     const uint32_t wpt = (((len + 3) >> 2) + NT - 1) / NT; // row words per thread
-                    if (P.small_tab && wpt <= 1) bigram_row_small<D, NT, 1>(cur, up, len, shift, bpp, sr);
-                    else if (P.small_tab && wpt <= 2) bigram_row_small<D, NT, 2>(cur, up, len, shift, bpp, sr);
+                    if (P.small_tab && wpt <= 1) bigram_row_small<D, NT, 1>(cur, up, len, shift, bpp, sr, P.h0_slots);
+                    else if ((SC & SC_HALF) || (P.small_tab && wpt <= 2)) bigram_row_small<D, NT, 2>(cur, up, len, shift, bpp, sr, P.h0_slots);
                     else if (wpt <= 1) bigram_row<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
                     else if (wpt <= 2) bigram_row<D, NT, 2>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
                     else if (wpt <= 4) bigram_row<D, NT, 4>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
@@ -920,6 +919,7 @@ KernelFn pick_sc(int sc) {
     case SC_MINSUM: return k_fast<D, SC_MINSUM>;
     case SC_ENTROPY: return k_fast<D, SC_ENTROPY>;
     case SC_BIGRAM: return k_fast<D, SC_BIGRAM>;
+    case SC_BIGRAM | SC_HALF: return k_fast<D, SC_BIGRAM | SC_HALF>;
     default: return k_fast<D, SC_MINSUM | SC_ENTROPY | SC_BIGRAM>;
     }
 }
@@ -934,15 +934,14 @@ bool fast_supported(const Geom &g, const StrategySet &set) {
     if (g.alpha_bytes != 0 || g.total_rows == 0) return false;
     if (g.bpp != 1 && g.bpp != 2 && g.bpp != 3 && g.bpp != 4 && g.bpp != 6 && g.bpp != 8) return false;
     const int sc = kernel_sc(scorers_needed(set));
-    if (smem_bytes_for(sc, slot_bytes(g), false) > SMEM_LIMIT) return false;
+    if (smem_bytes_for(sc, slot_bytes(g), 0) > SMEM_LIMIT) return false;
     if ((sc & SC_BIGRAM) && g.max_len > 32768u) return false; // <= 8 row words per thread; u16 counters
     return true;
 }
 
 cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_data, size_t n_images,
                         const StrategySet &set) {
-    const int sc = kernel_sc(scorers_needed(set));
-    const int nt = threads_for(sc);
+    int sc = kernel_sc(scorers_needed(set));
     FastParams P;
     P.g = g;
     P.set = set;
@@ -950,10 +949,20 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
     P.n_images = n_images;
     P.rb = slot_bytes(g);
     P.shift = 8 * (g.bpp % 4);
-    P.small_tab = (sc & SC_BIGRAM) && g.max_len <= 8192 && smem_bytes_for(sc, P.rb, true) <= SMEM_LIMIT;
+    // bigram scorer, rows <= 8192 bytes: hash of whole rows (> 2 slots per window) + dense tables + outlier hashes
+    uint32_t h0 = 1024;
+    while (h0 < 2 * g.max_len) h0 *= 2;
+    P.small_tab = (sc & SC_BIGRAM) && g.max_len <= 8192 && smem_bytes_for(sc, P.rb, h0) <= SMEM_LIMIT;
+    P.h0_slots = P.small_tab ? h0 : 0;
+    // ... and with rows <= 4096 bytes two 512-thread CTAs fit an SM (two rows in flight: one CTA's barriers and table
+    // sweeps overlap the other's counting)
+    const uint32_t two_per_sm = (233472u / 2 - 1024u) & ~127u;
+    if (sc == SC_BIGRAM && P.small_tab && g.max_len <= 4096 && smem_bytes_for(sc, P.rb, h0, 3) <= two_per_sm) sc |= SC_HALF;
+    const int nt = threads_for(sc);
     // a fourth ring slot removes the end-of-row barrier; take it when it does not cost occupancy (rows <= 16 KB)
-    P.nslot = (sc != 0 && P.rb <= 16448 && smem_bytes_for(sc, P.rb, P.small_tab != 0, 4) <= SMEM_LIMIT) ? 4 : 3;
-    const uint32_t smem = smem_bytes_for(sc, P.rb, P.small_tab != 0, P.nslot);
+    const uint32_t budget = (sc & SC_HALF) ? two_per_sm : SMEM_LIMIT;
+    P.nslot = (sc != 0 && P.rb <= 16448 && smem_bytes_for(sc, P.rb, P.h0_slots, 4) <= budget) ? 4 : 3;
+    const uint32_t smem = smem_bytes_for(sc, P.rb, P.h0_slots, P.nslot);
     KernelFn fn = pick_kernel((int)(g.bpp / 4), sc);
     cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
