@@ -70,8 +70,9 @@ __device__ __forceinline__ uint32_t paeth(uint32_t a, uint32_t b, uint32_t c) {
 
 // ilog2i, src/filters/strategies.rs:269-272 (i >= 1)
 __device__ __forceinline__ uint32_t ilog2i(uint32_t i) {
-    uint32_t lg = 31u - (uint32_t)__clz((int)i);
-    return i * lg + ((i - (1u << lg)) << 1);
+    // i * lg + ((i - 2^lg) << 1), written as one multiply-add: i * (lg + 2) - 2^(lg + 1)
+    const uint32_t lg = 31u - (uint32_t)__clz((int)i);
+    return i * (lg + 2u) - (2u << lg);
 }
 
 // residual of one byte under filter f (src/filters/mod.rs:63-110). left/upleft are 0 for the first bpp bytes,
