@@ -583,31 +583,45 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
         constexpr int TPT = NT / 4; // threads per trial
         const uint32_t f = 1 + threadIdx.x / TPT;
         uint32_t d = 0, e = 0;
-        for (uint32_t w = threadIdx.x % TPT; w < SMALL_WORDS; w += TPT) {
-            uint32_t c0 = 0, c1 = 0;
+        // four words (eight counters) at a time; most groups are empty in every replica.  A replica's rotation
+        // (word ^ (rp << 3)) keeps aligned groups of four words together: group ^ (rp << 1).
+        for (uint32_t g = threadIdx.x % TPT; g < SMALL_WORDS / 4; g += TPT) {
+            uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            bool any = false;
 #pragma unroll
             for (int rp = 0; rp < SMALL_REP; rp++) {
-                uint32_t *cell = sm.small + ((f - 1) * SMALL_REP + rp) * SMALL_WORDS + (w ^ (uint32_t)(rp << 3));
-                const uint32_t v = *cell;
-                if (v) {
-                    *cell = 0;
-                    c0 += v & 0xFFFFu;
-                    c1 += v >> 16;
+                uint4 *cell = reinterpret_cast<uint4 *>(sm.small + ((f - 1) * SMALL_REP + rp) * SMALL_WORDS) + (g ^ (uint32_t)(rp << 1));
+                const uint4 v = *cell;
+                if (v.x | v.y | v.z | v.w) {
+                    *cell = make_uint4(0, 0, 0, 0);
+                    any = true;
+                    c[0] += v.x & 0xFFFFu; c[1] += v.x >> 16;
+                    c[2] += v.y & 0xFFFFu; c[3] += v.y >> 16;
+                    c[4] += v.z & 0xFFFFu; c[5] += v.z >> 16;
+                    c[6] += v.w & 0xFFFFu; c[7] += v.w >> 16;
                 }
             }
-            d += (c0 != 0) + (c1 != 0);
-            e += (c0 ? ilog2i(c0) : 0u) + (c1 ? ilog2i(c1) : 0u);
+            if (any) {
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if (c[q]) {
+                        d += 1;
+                        e += ilog2i(c[q]);
+                    }
+            }
         }
         // the trial's outlier hash table: counted unless the trial is flagged (then only cleared)
         const bool hashed = sm.s_out_()[f] == 0;
-        for (uint32_t w = threadIdx.x % TPT; w < HSLOTS; w += TPT) {
-            uint32_t *cell = sm.ohash + (f - 1) * HSLOTS + w;
-            const uint32_t v = *cell;
-            if (v) {
-                *cell = 0;
+        for (uint32_t g = threadIdx.x % TPT; g < HSLOTS / 4; g += TPT) {
+            uint4 *cell = reinterpret_cast<uint4 *>(sm.ohash + (f - 1) * HSLOTS) + g;
+            const uint4 v = *cell;
+            if (v.x | v.y | v.z | v.w) {
+                *cell = make_uint4(0, 0, 0, 0);
                 if (hashed) {
-                    d += 1;
-                    e += ilog2i(v & 0xFFFFu);
+                    if (v.x) { d += 1; e += ilog2i(v.x & 0xFFFFu); }
+                    if (v.y) { d += 1; e += ilog2i(v.y & 0xFFFFu); }
+                    if (v.z) { d += 1; e += ilog2i(v.z & 0xFFFFu); }
+                    if (v.w) { d += 1; e += ilog2i(v.w & 0xFFFFu); }
                 }
             }
         }
