@@ -162,10 +162,9 @@ __device__ __forceinline__ uint32_t residual_at(int f, const uint8_t *cur, const
 // XOR-swizzled with the first byte so that the bank depends on both bytes: runs like "(x, 0)" (every pixel's alpha
 // residual) would otherwise put a whole warp on one bank.
 __device__ __forceinline__ uint32_t big_word(uint32_t bg) { return (bg >> 1) ^ ((bg >> 8) & 31u); }
-// dense in-range tables: 32x32 keys (both bytes in [-16,15]) = 512 words, SMALL_REP lane-selected replicas per trial
-constexpr int SMALL_REP = 4;
-constexpr uint32_t SMALL_WORDS = 512;
-__device__ __forceinline__ uint32_t small_word(uint32_t idx) { return (idx >> 1) ^ ((idx >> 5) & 15u); }
+// dense tables: 32x32 keys as u32 counters, 2 lane-selected replicas each.  Trials 1..4: both bytes in [-16,15];
+// trial 0: the low five bits of both raw bytes (a coarsening that bounds the trial's scores, see bigram_row_small)
+constexpr uint32_t DENSE_WORDS = 4 * 2 * 1024 + 2 * 1024; // trials 1..4, then the coarse table of trial 0
 
 // ---- shared-memory carve-up --------------------------------------------------------------------------------------
 struct Smem {
@@ -179,25 +178,31 @@ struct Smem {
     uint8_t *rows;     // 3 slots of rb bytes
     uint32_t *hist;    // [5][HIST_REP][256]
     uint32_t *table;   // 32768 words = 65536 u16 counters, or (small_tab) the h0_slots-word hash table of whole rows
-    uint32_t *small;   // [4][SMALL_REP][512] words: 32x32 u16 counter tables (in-range bigrams of trials 1..4), optional
+    uint32_t *small;   // DENSE_WORDS counters of the in-range bigrams of trials 1..4 (layout: dense_off), optional
     uint32_t *ohash;   // [4][HSLOTS] outlier bigrams of trials 1..4: open-addressing tables of (key << 16 | count)
 };
+constexpr uint32_t SMALL_BYTES = DENSE_WORDS * 4 + 4 * HSLOTS * 4; // dense tables + outlier hashes
+// h0_slots != 0 selects the small-table layout: header | dense tables | outlier hashes | h0 | row ring | histograms.
+// The tables come first so that their shared-memory offsets are compile-time constants (immediates of the atomics).
+// Otherwise: header | row ring | histograms | 65536-entry bigram table.
 template <int SC>
-__device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot, uint32_t table_words) {
+__device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot, uint32_t h0_slots) {
     Smem s;
     s.bar = reinterpret_cast<uint64_t *>(base);
     uint32_t *u = reinterpret_cast<uint32_t *>(base + 64);
     s.sc = u; // set 0; sets 1 and 2 follow at SCORE_WORDS strides
-    s.rows = base + SMEM_HDR;
-    uint8_t *p = s.rows + nslot * (size_t)rb;
+    uint8_t *p = base + SMEM_HDR;
+    s.small = reinterpret_cast<uint32_t *>(p);
+    s.ohash = s.small + DENSE_WORDS;
+    s.table = s.ohash + 4 * HSLOTS;
+    if ((SC & SC_BIGRAM) && h0_slots) p += SMALL_BYTES + h0_slots * 4;
+    s.rows = p;
+    p += nslot * (size_t)rb;
     s.hist = reinterpret_cast<uint32_t *>(p);
     if (SC & SC_ENTROPY) p += 5 * HIST_REP * 256 * 4;
-    s.table = reinterpret_cast<uint32_t *>(p);
-    s.small = s.table + table_words;
-    s.ohash = s.small + 4 * SMALL_REP * SMALL_WORDS;
+    if (!((SC & SC_BIGRAM) && h0_slots)) s.table = reinterpret_cast<uint32_t *>(p);
     return s;
 }
-constexpr uint32_t SMALL_BYTES = 4 * SMALL_REP * SMALL_WORDS * 4 + 4 * HSLOTS * 4; // dense tables + outlier hashes
 // h0_slots != 0: the small-table layout (hash of whole rows + dense tables + outlier hashes); 0: the 65536-entry table
 __host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, uint32_t h0_slots, uint32_t nslot = 3) {
     uint32_t b = SMEM_HDR + nslot * rb;
@@ -463,174 +468,256 @@ __device__ __forceinline__ bool ohash_add(uint32_t *h, uint32_t key) {
 __device__ __forceinline__ uint32_t range_code4(uint32_t r) { // per byte: (b + 16) mod 256 (no carries across bytes)
     return ((r & 0x7F7F7F7Fu) + 0x10101010u) ^ (r & 0x80808080u);
 }
-template <int D, int NT, int WPT>
+// ilog2i that is also valid for i == 0 (returns 0): no branch in the table sweeps.  PTX shl clamps the shift amount,
+// so for i == 0 (lg = -1) the subtrahend is 0 and the product is 0 * 1.
+__device__ __forceinline__ uint32_t ilog2i_z(uint32_t i) {
+    const uint32_t lg = 31u - (uint32_t)__clz((int)i);
+    uint32_t sh;
+    asm("shl.b32 %0, %1, %2;" : "=r"(sh) : "r"(2u), "r"(lg));
+    return i * (lg + 2u) - sh;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { // full prmt (sign-replicate nibbles kept)
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ void smem_inc(uint32_t addr) { // no-return add of 1 on a shared-window byte address
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
+}
+// Dense tables, trials 1..4: u32 counters, two lane-selected replicas per trial, 32 KB in all.  Byte offset of the
+// counter of window (first, second) -- both as range codes 0..31 -- of trial f in replica rep:
+//     first << 10 | (f-1) << 8 | rep << 7 | (second ^ first ^ 16*rep) << 2
+// i.e. the high byte of the offset is (first << 2 | f-1) and the low byte (swizzled second << 2 | rep << 7): one prmt
+// per window picks the two bytes out of two pre-scaled words, one red.shared per window counts it.  The bank is
+// second ^ first (^ 16 for replica 1), so runs like "(x, alpha residual 0)" spread over the banks.
+__device__ __forceinline__ uint32_t dense_off(uint32_t f, uint32_t rep, uint32_t first, uint32_t second) {
+    return (first << 10) | ((f - 1u) << 8) | (rep << 7) | ((second ^ first ^ (rep << 4)) << 2);
+}
+
+// One row word (four windows) of trials 1..4.  tr = range codes of the word's residual bytes, tpr = codes of the stream
+// bytes in front of them -- both with their bytes rotated by the lane's window rotation (every step is bytewise, so the
+// rotation only changes which window a given red.shared of the warp counts).
+template <int F>
+__device__ __forceinline__ void dense_word(uint32_t tr, uint32_t tpr, uint32_t dense_base, uint32_t c1, uint32_t c2) {
+    const uint32_t hi = tpr * 4u + (uint32_t)(F - 1) * 0x01010101u;
+    const uint32_t lo = (tr ^ tpr ^ c1) * 4u + c2; // c1 = rep * 0x10101010, c2 = rep * 0x80808080
+    smem_inc(dense_base + prmt(lo, hi, 0xCC40u));
+    smem_inc(dense_base + prmt(lo, hi, 0xDD51u));
+    smem_inc(dense_base + prmt(lo, hi, 0xEE62u));
+    smem_inc(dense_base + prmt(lo, hi, 0xFF73u));
+}
+// the same word window by window: tail words and words with an out-of-range byte (t, tprev unrotated)
+template <int F>
+__device__ __noinline__ void dense_word_slow(uint32_t t, uint32_t tprev, int valid, uint32_t dense_base, uint32_t rep,
+                                             uint32_t *ohash, uint32_t *s_out) {
+    uint32_t tp = tprev >> 24;
+    for (int j = 0; j < 4; j++) {
+        const uint32_t tj = (t >> (8 * j)) & 255u;
+        if (j < valid) {
+            if (((tp | tj) & 0xE0u) == 0) {
+                smem_inc(dense_base + dense_off(F, rep, tp, tj));
+            } else if (*(volatile uint32_t *)&s_out[F] == 0) {
+                // outliers go to the trial's hash table until an insert finds it crowded; from then on the
+                // trial is flagged and all its outliers are counted in h0 after the barrier
+                if (!ohash_add(ohash + (F - 1) * HSLOTS, (((tp + 240u) & 255u) << 8) | ((tj + 240u) & 255u)))
+                    *(volatile uint32_t *)&s_out[F] = 1u;
+            }
+        }
+        tp = tj;
+    }
+}
+
+// trial 0 on coarse keys (low five bits of both raw bytes): offset first << 8 | rep << 7 | (second ^ first ^ 16*rep) << 2
+// inside the 8 KB behind the tables of trials 1..4
+__device__ __forceinline__ void dense_word0(uint32_t xr, uint32_t pr, uint32_t dense_base, uint32_t c1, uint32_t c2) {
+    const uint32_t hi = pr & 0x1F1F1F1Fu;
+    const uint32_t lo = (((xr ^ pr) & 0x1F1F1F1Fu) ^ c1) * 4u + c2;
+    smem_inc(dense_base + 32768u + prmt(lo, hi, 0xCC40u));
+    smem_inc(dense_base + 32768u + prmt(lo, hi, 0xDD51u));
+    smem_inc(dense_base + 32768u + prmt(lo, hi, 0xEE62u));
+    smem_inc(dense_base + 32768u + prmt(lo, hi, 0xFF73u));
+}
+__device__ __noinline__ void dense_word0_slow(uint32_t x, uint32_t xprev, int valid, uint32_t dense_base, uint32_t rep) {
+    uint32_t p = (xprev >> 24) & 31u;
+    for (int j = 0; j < valid && j < 4; j++) {
+        const uint32_t b = (x >> (8 * j)) & 31u;
+        smem_inc(dense_base + 32768u + ((p << 8) | (rep << 7) | ((b ^ p ^ (rep << 4)) << 2)));
+        p = b;
+    }
+}
+
+// Exact Bigrams/BigEnt scores of trial 0 (the raw row), for the rows whose coarse bounds could not rule it out: every
+// window goes to the hash table h0 (clean on entry and on exit); distinct keys and entropy are accumulated in
+// s_bgc[5] / s_bge[5] (zero on entry).  Two CTA-wide barriers.
+template <int NT>
+__device__ __noinline__ void bigram_exact0(const uint8_t *cur, uint32_t len, uint32_t *h0, uint32_t h0_slots, uint32_t *s_bgc,
+                                           uint32_t *s_bge) {
+    const uint32_t hmask = h0_slots - 1, hshift = (uint32_t)__clz((int)h0_slots) + 1;
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur);
+    for (uint32_t k = threadIdx.x; 4 * k < len; k += NT) {
+        const uint32_t x = cw[k];
+        uint32_t p = cw[(int)k - 1] >> 24; // word -1 is the zero pad: the filter-type byte 0 in front of the row
+        const int valid = (int)len - 4 * (int)k;
+        for (int j = 0; j < 4 && j < valid; j++) {
+            const uint32_t b = (x >> (8 * j)) & 255u;
+            h0_add(h0, (p << 8) | b, hshift, hmask);
+            p = b;
+        }
+    }
+    __syncthreads();
+    uint32_t d = 0, e = 0;
+    h0_sweep<NT>(h0, h0_slots, d, e);
+    d = warp_sum(d);
+    e = warp_sum(e);
+    if ((threadIdx.x & 31) == 0 && d) {
+        atomicAdd(&s_bgc[5], d);
+        atomicAdd(&s_bge[5], e);
+    }
+    __syncthreads();
+}
+
+// Per row (rows <= 8192 bytes):
+//  * trials 1..4: a window whose two stream bytes both lie in [-16, 15] (as i8) is counted in a dense 32x32 table of
+//    its trial (two lane-selected replicas, bank = first ^ second); the remaining (outlier) windows go to a small
+//    open-addressing hash table of (key, count) per trial;
+//  * trial 0 (None: the raw bytes, spread over the whole byte range) is counted on COARSE keys -- the low five bits of
+//    both bytes -- in a fifth dense table.  Merging keys can only lower the number of distinct keys and raise
+//    sum ilog2i(count) (ilog2i is convex with ilog2i(0) = 0, hence superadditive), so the coarse scores are a lower
+//    bound of the trial's Bigrams score and an upper bound of its BigEnt score.  None is first in RowFilter::ALL and
+//    wins ties, so it is chosen iff d0 <= min d_f resp. e0 >= max e_f; when the bounds already say it loses (the
+//    usual case for photographic rows) its exact scores are never needed.  Otherwise the caller runs bigram_exact0.
+//  * after one barrier every table is swept (and cleared): non-zero counters are the distinct bigrams, their counts
+//    give the entropy.  No ownership bookkeeping, nothing kept in registers across the barrier;
+//  * a trial whose outliers crowd its small hash in some row (noise-like data) is flagged; its outliers are then
+//    re-derived from the staged row and counted in h0, trial by trial.
+// Exact for any data: every window is counted in exactly one structure, and their key sets are disjoint.
+template <int D, int NT>
 __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
                                                  const Smem &sm, uint32_t h0_slots) {
-    const uint32_t nwords = (len + 3) >> 2;
-    const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur), *uw = reinterpret_cast<const uint32_t *>(up);
+    const uint32_t nwords = (len + 3) >> 2, npairs = (nwords + 1) >> 1;
     uint32_t *h0 = sm.table;
-    const uint32_t hmask = h0_slots - 1, hshift = (uint32_t)__clz((int)h0_slots) + 1; // 32 - log2(slots)
-#pragma unroll
-    for (int i = 0; i < WPT; i++) {
-        const uint32_t k = threadIdx.x + i * NT;
-        const int kk = (int)k;
-        uint32_t x = 0, l = 0, u = 0, ul = 0;
-        if (k < nwords) {
-            x = cw[kk];
-            u = uw[kk];
-            l = D == 2 ? cw[kk - 2] : D == 1 ? __funnelshift_l(cw[kk - 2], cw[kk - 1], shift)
-                                             : __funnelshift_l(cw[kk - 1], cw[kk], shift);
-            ul = D == 2 ? uw[kk - 2] : D == 1 ? __funnelshift_l(uw[kk - 2], uw[kk - 1], shift)
-                                              : __funnelshift_l(uw[kk - 1], uw[kk], shift);
-        }
-        uint32_t r[5], pv[5];
-        r[0] = x;
-        r[1] = __vsub4(x, l);
-        r[2] = __vsub4(x, u);
-        r[3] = __vsub4(x, __vhaddu4(l, u));
-        r[4] = __vsub4(x, paeth4(l, u, ul));
-#pragma unroll
-        for (int f = 0; f < 5; f++) pv[f] = __shfl_up_sync(0xffffffffu, r[f] >> 24, 1);
-        if ((threadIdx.x & 31) == 0) { // lane 0 has no neighbour: the filter id in front of word 0, else one scalar pixel
-            if (k == 0) {
-#pragma unroll
-                for (int f = 0; f < 5; f++) pv[f] = (uint32_t)f;
-            } else if (k < nwords) {
-                const int q = 4 * kk - 1;
-                const uint32_t cx = cur[q], cl = cur[q - bpp], cu = up[q], cul = up[q - bpp];
-                pv[0] = cx;
-                pv[1] = (cx - cl) & 255u;
-                pv[2] = (cx - cu) & 255u;
-                pv[3] = (cx - ((cl + cu) >> 1)) & 255u;
-                pv[4] = (cx - paeth(cl, cu, cul)) & 255u;
-            }
-        }
-        const int valid = (int)len - 4 * kk;
-        // trial 0: the four windows' claims go out together, collisions / repeats are settled afterwards
-        {
-            uint32_t tag[4], slot[4], old[4];
-            // keys (prev << 8 | byte) of windows 0..3: bytes 0..3 of (x << 8 | pv) paired with bytes of x
-            const uint32_t pw = __byte_perm(x, pv[0], 0x2104);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t key = (((pw >> (8 * j)) & 255u) << 8) | ((x >> (8 * j)) & 255u);
-                tag[j] = (key + 1u) << 14;
-                slot[j] = h0_slot(key, hshift);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) old[j] = j < valid ? atomicCAS(&h0[slot[j]], 0u, tag[j] | 1u) : 0u;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (old[j] != 0) h0_collide(h0, slot[j], tag[j], old[j], hmask);
-        }
-#pragma unroll
-        for (int f = 1; f < 5; f++) {
-            // Byte-SIMD form of the four windows of this word: t = range codes of its bytes, tpw = codes of the bytes
-            // just before them; a window is in range when neither code has a bit above the low five.
-            const uint32_t t = range_code4(r[f]);
-            const uint32_t tpw = __byte_perm(t, (pv[f] + 16u) & 255u, 0x2104);
-            const uint32_t fl = (t | tpw) & 0xE0E0E0E0u;
-            // replica by lane; each replica is additionally rotated by 8 banks (its base is a multiple of 32 words, so
-            // without the rotation the four replicas of one counter would share a bank)
-            const uint32_t rp = threadIdx.x & (SMALL_REP - 1), rot = rp << 3;
-            uint32_t *tab = sm.small + ((f - 1) * SMALL_REP + rp) * SMALL_WORDS;
-            if (valid >= 4 && fl == 0) { // the common case: all four windows in range -> no per-window branches
-                // table index first*32 + second for windows 0,2 (16-bit lanes of e) and 1,3 (lanes of o)
-                const uint32_t e = (tpw & 0x00FF00FFu) * 32u + (t & 0x00FF00FFu);
-                const uint32_t o = ((tpw >> 8) & 0x00FF00FFu) * 32u + ((t >> 8) & 0x00FF00FFu);
-                // small_word() ^ rot on both lanes at once: (idx >> 1) ^ ((idx >> 5) & 15) ^ rot
-                const uint32_t rot2 = rot * 0x00010001u;
-                const uint32_t we = ((e >> 1) & 0x01FF01FFu) ^ ((e >> 5) & 0x000F000Fu) ^ rot2;
-                const uint32_t wo = ((o >> 1) & 0x01FF01FFu) ^ ((o >> 5) & 0x000F000Fu) ^ rot2;
-                atomicAdd(&tab[we & 0xFFFFu], 1u + (e & 1u) * 0xFFFFu);
-                atomicAdd(&tab[wo & 0xFFFFu], 1u + (o & 1u) * 0xFFFFu);
-                atomicAdd(&tab[we >> 16], 1u + ((e >> 16) & 1u) * 0xFFFFu);
-                atomicAdd(&tab[wo >> 16], 1u + ((o >> 16) & 1u) * 0xFFFFu);
+    const uint32_t hmask = h0_slots - 1, hshift = (uint32_t)__clz((int)h0_slots) + 1; // flagged path (h0_add)
+    const uint32_t lane = threadIdx.x & 31u, rep = (lane >> 2) & 1u;
+    const uint32_t dense_base = smem_u32(sm.small);
+    const uint32_t c1 = rep * 0x10101010u, c2 = rep * 0x80808080u;
+    // Window rotation: byte j of a rotated word is byte (j + lane) & 3 of the word, so that the 32 lanes of one atomic
+    // mix the four channel pairs of RGBA instead of all hitting the same (few-valued) pair.  rt rotates a word; rp builds
+    // the rotated "bytes in front" word from (word, previous word): byte m of it is m ? word.byte[m-1] : previous.byte[3].
+    const uint32_t r0 = lane & 3u;
+    const uint32_t rt = (0x32103210u >> (4 * r0)) & 0xFFFFu, rp = (0x21072107u >> (4 * r0)) & 0xFFFFu;
+    // thread t owns the row words 2t and 2t+1 (one 8-byte load per row and neighbour)
+    for (uint32_t pr = threadIdx.x; pr < ((npairs + 31u) & ~31u); pr += NT) {
+        uint32_t x[2] = {0, 0}, u[2] = {0, 0}, l[2] = {0, 0}, ul[2] = {0, 0};
+        const int k = 2 * (int)pr;
+        if (pr < npairs) {
+            // words k-2 .. k+1 are addressable: a slot has 32 zero bytes in front of the row and 16+ behind it
+            const uint2 cx = *reinterpret_cast<const uint2 *>(cur + 4 * k), cp = *reinterpret_cast<const uint2 *>(cur + 4 * k - 8);
+            const uint2 ux = *reinterpret_cast<const uint2 *>(up + 4 * k), upv = *reinterpret_cast<const uint2 *>(up + 4 * k - 8);
+            x[0] = cx.x; x[1] = cx.y; u[0] = ux.x; u[1] = ux.y;
+            if (D == 2) { l[0] = cp.x; l[1] = cp.y; ul[0] = upv.x; ul[1] = upv.y; }
+            else if (D == 1) {
+                l[0] = __funnelshift_l(cp.x, cp.y, shift); l[1] = __funnelshift_l(cp.y, cx.x, shift);
+                ul[0] = __funnelshift_l(upv.x, upv.y, shift); ul[1] = __funnelshift_l(upv.y, ux.x, shift);
             } else {
-                uint32_t tp = tpw & 255u;
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t tj = (t >> (8 * j)) & 255u;
-                    if (j < valid) {
-                        if (((tp | tj) & 0xE0u) == 0) {
-                            const uint32_t idx = (tp << 5) | tj;
-                            atomicAdd(&tab[small_word(idx) ^ rot], (idx & 1u) ? 0x10000u : 1u);
-                        } else if (*(volatile uint32_t *)&sm.s_out_()[f] == 0) {
-                            // outliers go to the trial's hash table until an insert finds it crowded; from then on the
-                            // trial is flagged and all its outliers are counted in h0 after the barrier
-                            if (!ohash_add(sm.ohash + (f - 1) * HSLOTS, (((tp + 240u) & 255u) << 8) | ((tj + 240u) & 255u)))
-                                *(volatile uint32_t *)&sm.s_out_()[f] = 1u;
-                        }
+                l[0] = __funnelshift_l(cp.y, cx.x, shift); l[1] = __funnelshift_l(cx.x, cx.y, shift);
+                ul[0] = __funnelshift_l(upv.y, ux.x, shift); ul[1] = __funnelshift_l(ux.x, ux.y, shift);
+            }
+        }
+        // range codes (residual + 16 per byte) of the four filtered trials
+        uint32_t t[4][2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint32_t xc = __vadd4(x[i], 0x10101010u);
+            t[0][i] = __vsub4(xc, l[i]);
+            t[1][i] = __vsub4(xc, u[i]);
+            t[2][i] = __vsub4(xc, __vhaddu4(l[i], u[i]));
+            t[3][i] = __vsub4(xc, paeth4(l[i], u[i], ul[i]));
+        }
+        // stream byte in front of the pair: the last byte of the previous pair (neighbouring lane); lane 0 has no
+        // neighbour: the filter id in front of word 0, else one scalar pixel
+        uint32_t xprev = __shfl_up_sync(0xffffffffu, x[1], 1), tprev[4];
+#pragma unroll
+        for (int f = 0; f < 4; f++) tprev[f] = __shfl_up_sync(0xffffffffu, t[f][1], 1);
+        if (lane == 0) {
+            if (k == 0) {
+                xprev = 0;
+#pragma unroll
+                for (int f = 0; f < 4; f++) tprev[f] = (uint32_t)(f + 1 + 16) << 24;
+            } else if (pr < npairs) {
+                const int q = 4 * k - 1;
+                const uint32_t cx = cur[q], cl = cur[q - bpp], cu = up[q], cul = up[q - bpp];
+                xprev = cx << 24;
+                tprev[0] = (cx - cl + 16u) << 24;
+                tprev[1] = (cx - cu + 16u) << 24;
+                tprev[2] = (cx - ((cl + cu) >> 1) + 16u) << 24;
+                tprev[3] = (cx - paeth(cl, cu, cul) + 16u) << 24;
+            }
+        }
+        if (pr < npairs) {
+            const int valid0 = (int)len - 4 * k;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const int valid = valid0 - 4 * i;
+                if (valid <= 0) break;
+                const uint32_t xp = i ? x[0] : xprev;
+                if (valid >= 4) dense_word0(prmt(x[i], 0u, rt), prmt(x[i], xp, rp), dense_base, c1, c2);
+                else dense_word0_slow(x[i], xp, valid, dense_base, rep);
+#pragma unroll
+                for (int f = 0; f < 4; f++) {
+                    const uint32_t tp = i ? t[f][0] : tprev[f];
+                    const uint32_t tr = prmt(t[f][i], 0u, rt), tpr = prmt(t[f][i], tp, rp);
+                    if (valid >= 4 && ((tr | tpr) & 0xE0E0E0E0u) == 0) { // the common case: all four windows in range
+                        if (f == 0) dense_word<1>(tr, tpr, dense_base, c1, c2);
+                        if (f == 1) dense_word<2>(tr, tpr, dense_base, c1, c2);
+                        if (f == 2) dense_word<3>(tr, tpr, dense_base, c1, c2);
+                        if (f == 3) dense_word<4>(tr, tpr, dense_base, c1, c2);
+                    } else {
+                        if (f == 0) dense_word_slow<1>(t[f][i], tp, valid, dense_base, rep, sm.ohash, sm.s_out_());
+                        if (f == 1) dense_word_slow<2>(t[f][i], tp, valid, dense_base, rep, sm.ohash, sm.s_out_());
+                        if (f == 2) dense_word_slow<3>(t[f][i], tp, valid, dense_base, rep, sm.ohash, sm.s_out_());
+                        if (f == 3) dense_word_slow<4>(t[f][i], tp, valid, dense_base, rep, sm.ohash, sm.s_out_());
                     }
-                    tp = tj;
                 }
             }
         }
     }
     __syncthreads();
-    // trial 0: sweep h0
+    // sweep the dense tables (sum of the two replicas), four keys at a time, and the outlier hashes
     {
-        uint32_t d = 0, e = 0;
-        h0_sweep<NT>(h0, h0_slots, d, e);
-        d = warp_sum(d);
-        e = warp_sum(e);
-        if ((threadIdx.x & 31) == 0 && d) {
-            atomicAdd(&sm.s_bgc_()[0], d);
-            atomicAdd(&sm.s_bge_()[0], e);
-        }
-    }
-    // trials 1..4: sweep the dense tables (sum of the replicas) and the outlier hash, a quarter of the CTA per trial
-    {
-        constexpr int TPT = NT / 4; // threads per trial
-        const uint32_t f = 1 + threadIdx.x / TPT;
-        uint32_t d = 0, e = 0;
-        // four words (eight counters) at a time; most groups are empty in every replica.  A replica's rotation
-        // (word ^ (rp << 3)) keeps aligned groups of four words together: group ^ (rp << 1).
-        for (uint32_t g = threadIdx.x % TPT; g < SMALL_WORDS / 4; g += TPT) {
-            uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            bool any = false;
-#pragma unroll
-            for (int rp = 0; rp < SMALL_REP; rp++) {
-                uint4 *cell = reinterpret_cast<uint4 *>(sm.small + ((f - 1) * SMALL_REP + rp) * SMALL_WORDS) + (g ^ (uint32_t)(rp << 1));
+        uint4 *dn = reinterpret_cast<uint4 *>(sm.small);
+        // q < 1024: trial-1 : 2 | first : 5 | group of four seconds : 3;  q >= 1024: trial 0, first : 5 | group : 3
+        for (uint32_t q = threadIdx.x; q < 1280u; q += NT) {
+            const uint32_t f = q < 1024u ? 1u + (q >> 8) : 0u, first = (q >> 3) & 31u, g = q & 7u;
+            uint4 *c0 = dn + (f ? first * 64u + (f - 1u) * 16u : 2048u + first * 16u) + g, *c1 = c0 - g + 8u + (g ^ 4u);
+            const uint4 a = *c0, b = *c1;
+            *c0 = make_uint4(0, 0, 0, 0);
+            *c1 = make_uint4(0, 0, 0, 0);
+            const uint32_t n0 = a.x + b.x, n1 = a.y + b.y, n2 = a.z + b.z, n3 = a.w + b.w;
+            uint32_t d = (n0 != 0) + (n1 != 0) + (n2 != 0) + (n3 != 0);
+            uint32_t e = ilog2i_z(n0) + ilog2i_z(n1) + ilog2i_z(n2) + ilog2i_z(n3);
+            // the trial's outlier hash table (HSLOTS / 4 cells, one per thread of the trial's first 128): counted unless
+            // the trial is flagged (then only cleared)
+            const uint32_t w = q & 255u;
+            if (f && w < HSLOTS / 4) {
+                uint4 *cell = reinterpret_cast<uint4 *>(sm.ohash + (f - 1) * HSLOTS) + w;
                 const uint4 v = *cell;
                 if (v.x | v.y | v.z | v.w) {
                     *cell = make_uint4(0, 0, 0, 0);
-                    any = true;
-                    c[0] += v.x & 0xFFFFu; c[1] += v.x >> 16;
-                    c[2] += v.y & 0xFFFFu; c[3] += v.y >> 16;
-                    c[4] += v.z & 0xFFFFu; c[5] += v.z >> 16;
-                    c[6] += v.w & 0xFFFFu; c[7] += v.w >> 16;
-                }
-            }
-            if (any) {
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    if (c[q]) {
-                        d += 1;
-                        e += ilog2i(c[q]);
+                    if (sm.s_out_()[f] == 0) {
+                        if (v.x) { d += 1; e += ilog2i(v.x & 0xFFFFu); }
+                        if (v.y) { d += 1; e += ilog2i(v.y & 0xFFFFu); }
+                        if (v.z) { d += 1; e += ilog2i(v.z & 0xFFFFu); }
+                        if (v.w) { d += 1; e += ilog2i(v.w & 0xFFFFu); }
                     }
-            }
-        }
-        // the trial's outlier hash table: counted unless the trial is flagged (then only cleared)
-        const bool hashed = sm.s_out_()[f] == 0;
-        for (uint32_t g = threadIdx.x % TPT; g < HSLOTS / 4; g += TPT) {
-            uint4 *cell = reinterpret_cast<uint4 *>(sm.ohash + (f - 1) * HSLOTS) + g;
-            const uint4 v = *cell;
-            if (v.x | v.y | v.z | v.w) {
-                *cell = make_uint4(0, 0, 0, 0);
-                if (hashed) {
-                    if (v.x) { d += 1; e += ilog2i(v.x & 0xFFFFu); }
-                    if (v.y) { d += 1; e += ilog2i(v.y & 0xFFFFu); }
-                    if (v.z) { d += 1; e += ilog2i(v.z & 0xFFFFu); }
-                    if (v.w) { d += 1; e += ilog2i(v.w & 0xFFFFu); }
                 }
             }
-        }
-        // all 32 lanes of a warp sweep the same trial (TPT is a multiple of 32)
-        d = warp_sum(d);
-        e = warp_sum(e);
-        if ((threadIdx.x & 31) == 0 && d) {
-            atomicAdd(&sm.s_bgc_()[f], d);
-            atomicAdd(&sm.s_bge_()[f], e);
+            // all 32 lanes of a warp sweep the same trial (256 cells per trial)
+            d = warp_sum(d);
+            e = warp_sum(e);
+            if (lane == 0 && d) {
+                atomicAdd(&sm.s_bgc_()[f], d);
+                atomicAdd(&sm.s_bge_()[f], e);
+            }
         }
     }
     // flagged trials: their outlier windows, re-derived from the staged row, are counted in h0, one trial at a time
@@ -723,7 +810,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
     constexpr int NT = threads_for(SC);
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t NS = P.nslot;
-    const Smem sm = carve<SC>(smem_raw, P.rb, NS, P.small_tab ? P.h0_slots : 32768u);
+    const Smem sm = carve<SC>(smem_raw, P.rb, NS, P.small_tab ? P.h0_slots : 0u);
     const int tid = threadIdx.x;
     const int bpp = (int)P.g.bpp;
     const uint32_t shift = P.shift;
@@ -747,8 +834,12 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
     uint32_t parity = 0;  // bit s = phase to wait for on slot s
     uint32_t row_ctr = 0; // rows scored by this CTA so far: selects the score set
     const uint64_t total_items = P.n_images * (uint64_t)P.items_per_image;
-    bool any_heur = false;
-    for (int j = 0; j < P.set.k; j++) any_heur |= (P.set.s[j].kind != OXI_BASIC && P.set.s[j].kind != OXI_PREDEFINED);
+    bool any_heur = false, want_bg = false, want_be = false;
+    for (int j = 0; j < P.set.k; j++) {
+        any_heur |= (P.set.s[j].kind != OXI_BASIC && P.set.s[j].kind != OXI_PREDEFINED);
+        want_bg |= P.set.s[j].kind == OXI_BIGRAMS;
+        want_be |= P.set.s[j].kind == OXI_BIGENT;
+    }
     // With a 4-slot ring a slot is refilled two iterations after its last reader, and every scored row contains at
     // least one CTA-wide barrier, so the end-of-row barrier is only needed for the 3-slot ring / unscored rows.
     const bool row_end_barrier = NS < 4 || SC == 0 || !any_heur;
@@ -815,7 +906,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
 
             const uint32_t r = pd.row0 + k;
             const uint64_t in_off = pd.in_base + (uint64_t)k * len;
-            bool heur = false;
+            bool heur = false, need0 = false;
             // score set of this row; the set of the row after next is cleared here, before this row's barriers:
             // its last readers (decisions two rows ago) are behind the previous row's barriers
             Smem sr = sm;
@@ -831,8 +922,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
                 }
                 if (SC & SC_BIGRAM) {
                     const uint32_t wpt = (((len + 3) >> 2) + NT - 1) / NT; // row words per thread
-                    if (P.small_tab && wpt <= 1) bigram_row_small<D, NT, 1>(cur, up, len, shift, bpp, sr, P.h0_slots);
-                    else if ((SC & SC_HALF) || (P.small_tab && wpt <= 2)) bigram_row_small<D, NT, 2>(cur, up, len, shift, bpp, sr, P.h0_slots);
+                    if ((SC & SC_HALF) || P.small_tab) bigram_row_small<D, NT>(cur, up, len, shift, bpp, sr, P.h0_slots);
                     else if (wpt <= 1) bigram_row<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
                     else if (wpt <= 2) bigram_row<D, NT, 2>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
                     else if (wpt <= 4) bigram_row<D, NT, 4>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
@@ -853,6 +943,15 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
                 }
                 heur = __syncthreads_or(nz != 0) != 0;
                 row_ctr++;
+                if ((SC & SC_BIGRAM) && P.small_tab && heur) {
+                    // scores 0 are the coarse bounds of trial 0 (bigram_row_small); the exact pass runs only when they
+                    // leave open that None wins (it wins ties: d0 <= min d_f, e0 >= max e_f)
+                    const uint32_t *bc = sr.s_bgc_(), *be = sr.s_bge_();
+                    const uint32_t dmin = min(min(bc[1], bc[2]), min(bc[3], bc[4]));
+                    const int32_t emax = max(max((int32_t)be[1], (int32_t)be[2]), max((int32_t)be[3], (int32_t)be[4]));
+                    need0 = (want_bg && bc[0] <= dmin) || (want_be && (int32_t)be[0] >= emax);
+                    if (need0) bigram_exact0<NT>(cur, len, sm.table, P.h0_slots, sr.s_bgc_(), sr.s_bge_());
+                }
             }
 
             for (int j2 = 0; j2 < P.set.k; j2++) {
@@ -879,7 +978,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
                         uint32_t best = 0;
 #pragma unroll
                         for (int q = 0; q < 5; q++) {
-                            const uint32_t s = sr.s_bgc_()[q];
+                            const uint32_t s = sr.s_bgc_()[q == 0 && need0 ? 5 : q];
                             if (q == 0 || s < best) { best = s; f = q; }
                         }
                     } else { // Entropy / BigEnt: larger is better, strict '>' on i32 (strategies.rs:143,221)
@@ -887,7 +986,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
                         int32_t best = 0;
 #pragma unroll
                         for (int q = 0; q < 5; q++) {
-                            const int32_t s = (int32_t)sc[q];
+                            const int32_t s = (int32_t)sc[q == 0 && need0 && st.kind == OXI_BIGENT ? 5 : q];
                             if (q == 0 || s > best) { best = s; f = q; }
                         }
                     }
