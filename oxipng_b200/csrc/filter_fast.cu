@@ -27,12 +27,13 @@ namespace oxi {
 namespace {
 
 constexpr int SC_MINSUM = 1, SC_ENTROPY = 2, SC_BIGRAM = 4;
-constexpr int SC_HALF = 8; // with SC_BIGRAM alone, rows <= 4096 bytes: 512-thread CTAs, two resident per SM
+constexpr int SC_HALF = 8; // with SC_BIGRAM alone, rows <= 4096 bytes: 256-thread CTAs, four resident per SM
+constexpr int HALF_NT = 256, HALF_OCC = 4;
 constexpr int HIST_REP = 4;      // copies of each Entropy histogram (lane & 3) to thin same-address atomics
 constexpr uint32_t PAD = 32;     // zero bytes in front of every staged row (left/upleft of the first pixel)
-constexpr uint32_t SMEM_HDR = 1536;
+constexpr uint32_t SMEM_HDR = 1024;
 constexpr uint32_t SCORE_WORDS = 40;   // s_min/s_ent/s_bgc/s_bge/s_out, 8 words each; three sets rotate row by row
-constexpr uint32_t HSLOTS = 512;     // slots of a trial's outlier hash table (key << 16 | count)
+constexpr uint32_t HSLOTS = 256;     // slots of a trial's outlier hash table (key << 16 | count)
 constexpr int HPROBE = 8;            // probes before an insert gives up and sends the trial's outliers to the big table
 constexpr uint32_t SMEM_LIMIT = 232448; // 227 KB
 
@@ -50,7 +51,7 @@ struct FastParams {
     uint32_t small_tab; // bigram scorer: five dense 64x64 in-range tables are carved (rows <= 8192 bytes)
 };
 
-__host__ __device__ constexpr int threads_for(int sc) { return (sc & SC_HALF) ? 512 : (sc & SC_BIGRAM) ? 1024 : 256; }
+__host__ __device__ constexpr int threads_for(int sc) { return (sc & SC_HALF) ? HALF_NT : (sc & SC_BIGRAM) ? 1024 : 256; }
 
 // ---- PTX wrappers: mbarrier + 1-D bulk tensor-memory-accelerator copy -----------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -164,7 +165,7 @@ __device__ __forceinline__ uint32_t residual_at(int f, const uint8_t *cur, const
 __device__ __forceinline__ uint32_t big_word(uint32_t bg) { return (bg >> 1) ^ ((bg >> 8) & 31u); }
 // dense tables: 32x32 keys as u32 counters, 2 lane-selected replicas each.  Trials 1..4: both bytes in [-16,15];
 // trial 0: the low five bits of both raw bytes (a coarsening that bounds the trial's scores, see bigram_row_small)
-constexpr uint32_t DENSE_WORDS = 4 * 2 * 1024 + 2 * 1024; // trials 1..4, then the coarse table of trial 0
+constexpr uint32_t DENSE_WORDS = 4 * 2 * 1024 + 1024; // trials 1..4 (two replicas each), then the coarse table of trial 0
 
 // ---- shared-memory carve-up --------------------------------------------------------------------------------------
 struct Smem {
@@ -195,7 +196,10 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot
     s.small = reinterpret_cast<uint32_t *>(p);
     s.ohash = s.small + DENSE_WORDS;
     s.table = s.ohash + 4 * HSLOTS;
-    if ((SC & SC_BIGRAM) && h0_slots) p += SMALL_BYTES + h0_slots * 4;
+    if ((SC & SC_BIGRAM) && h0_slots) p += SMALL_BYTES + ((SC & SC_HALF) ? 0u : h0_slots * 4);
+    // SC_HALF: h0 (<= 8192 slots) is only used while the dense tables are swept clean and idle (exact pass of trial 0,
+    // flagged outliers) and leaves them clean: it lives in their memory
+    if (SC & SC_HALF) s.table = s.small;
     s.rows = p;
     p += nslot * (size_t)rb;
     s.hist = reinterpret_cast<uint32_t *>(p);
@@ -207,7 +211,7 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot
 __host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, uint32_t h0_slots, uint32_t nslot = 3) {
     uint32_t b = SMEM_HDR + nslot * rb;
     if (sc & SC_ENTROPY) b += 5 * HIST_REP * 256 * 4;
-    if (sc & SC_BIGRAM) b += h0_slots ? h0_slots * 4 + SMALL_BYTES : 65536 * 2;
+    if (sc & SC_BIGRAM) b += h0_slots ? ((sc & SC_HALF) ? 0u : h0_slots * 4) + SMALL_BYTES : 65536 * 2;
     return b;
 }
 
@@ -468,6 +472,29 @@ __device__ __forceinline__ bool ohash_add(uint32_t *h, uint32_t key) {
 __device__ __forceinline__ uint32_t range_code4(uint32_t r) { // per byte: (b + 16) mod 256 (no carries across bytes)
     return ((r & 0x7F7F7F7Fu) + 0x10101010u) ^ (r & 0x80808080u);
 }
+// the next row of the band, streamed into its ring slot (by TMA, or cooperatively for rows TMA cannot take)
+struct Prefetch {
+    bool on, tma;
+    uint8_t *dst;
+    const uint8_t *src;
+    uint32_t len;
+    uint64_t *bar;
+};
+template <int NT>
+__device__ __forceinline__ void coop_load_row(uint8_t *dst, const uint8_t *src, uint32_t len);
+template <int NT>
+__device__ __forceinline__ void issue_prefetch(const Prefetch &pf) {
+    if (!pf.on) return;
+    if (pf.tma) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(pf.bar, pf.len);
+            tma_load_1d(pf.dst, pf.src, pf.len, pf.bar);
+        }
+    } else {
+        coop_load_row<NT>(pf.dst, pf.src, pf.len);
+    }
+}
+
 // ilog2i that is also valid for i == 0 (returns 0): no branch in the table sweeps.  PTX shl clamps the shift amount,
 // so for i == 0 (lg = -1) the subtrahend is 0 and the product is 0 * 1.
 __device__ __forceinline__ uint32_t ilog2i_z(uint32_t i) {
@@ -527,21 +554,22 @@ __device__ __noinline__ void dense_word_slow(uint32_t t, uint32_t tprev, int val
     }
 }
 
-// trial 0 on coarse keys (low five bits of both raw bytes): offset first << 8 | rep << 7 | (second ^ first ^ 16*rep) << 2
-// inside the 8 KB behind the tables of trials 1..4
-__device__ __forceinline__ void dense_word0(uint32_t xr, uint32_t pr, uint32_t dense_base, uint32_t c1, uint32_t c2) {
-    const uint32_t hi = pr & 0x1F1F1F1Fu;
-    const uint32_t lo = (((xr ^ pr) & 0x1F1F1F1Fu) ^ c1) * 4u + c2;
+// trial 0 on coarse keys (low five bits of both raw bytes): one table of 32x32 counters (the keys of raw rows are
+// spread widely, a second replica buys little) in the 4 KB behind the tables of trials 1..4; offset
+// first << 7 | (second ^ first) << 2, i.e. high byte first >> 1, low byte (first & 1) << 7 | swizzled second << 2
+__device__ __forceinline__ void dense_word0(uint32_t xr, uint32_t pr, uint32_t dense_base) {
+    const uint32_t hi = (pr >> 1) & 0x0F0F0F0Fu;
+    const uint32_t lo = (pr & 0x01010101u) * 128u + ((xr ^ pr) & 0x1F1F1F1Fu) * 4u;
     smem_inc(dense_base + 32768u + prmt(lo, hi, 0xCC40u));
     smem_inc(dense_base + 32768u + prmt(lo, hi, 0xDD51u));
     smem_inc(dense_base + 32768u + prmt(lo, hi, 0xEE62u));
     smem_inc(dense_base + 32768u + prmt(lo, hi, 0xFF73u));
 }
-__device__ __noinline__ void dense_word0_slow(uint32_t x, uint32_t xprev, int valid, uint32_t dense_base, uint32_t rep) {
+__device__ __noinline__ void dense_word0_slow(uint32_t x, uint32_t xprev, int valid, uint32_t dense_base) {
     uint32_t p = (xprev >> 24) & 31u;
     for (int j = 0; j < valid && j < 4; j++) {
         const uint32_t b = (x >> (8 * j)) & 31u;
-        smem_inc(dense_base + 32768u + ((p << 8) | (rep << 7) | ((b ^ p ^ (rep << 4)) << 2)));
+        smem_inc(dense_base + 32768u + ((p << 7) | ((b ^ p) << 2)));
         p = b;
     }
 }
@@ -592,8 +620,8 @@ __device__ __noinline__ void bigram_exact0(const uint8_t *cur, uint32_t len, uin
 //    re-derived from the staged row and counted in h0, trial by trial.
 // Exact for any data: every window is counted in exactly one structure, and their key sets are disjoint.
 template <int D, int NT>
-__device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
-                                                 const Smem &sm, uint32_t h0_slots) {
+__device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
+                                                     const Smem &sm, uint32_t h0_slots, const Prefetch &pf) {
     const uint32_t nwords = (len + 3) >> 2, npairs = (nwords + 1) >> 1;
     uint32_t *h0 = sm.table;
     const uint32_t hmask = h0_slots - 1, hshift = (uint32_t)__clz((int)h0_slots) + 1; // flagged path (h0_add)
@@ -605,6 +633,7 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
     // the rotated "bytes in front" word from (word, previous word): byte m of it is m ? word.byte[m-1] : previous.byte[3].
     const uint32_t r0 = lane & 3u;
     const uint32_t rt = (0x32103210u >> (4 * r0)) & 0xFFFFu, rp = (0x21072107u >> (4 * r0)) & 0xFFFFu;
+    uint32_t nz = 0; // OR of this thread's row bytes (all-zero rows short-circuit to None, png/mod.rs:398-404)
     // thread t owns the row words 2t and 2t+1 (one 8-byte load per row and neighbour)
     for (uint32_t pr = threadIdx.x; pr < ((npairs + 31u) & ~31u); pr += NT) {
         uint32_t x[2] = {0, 0}, u[2] = {0, 0}, l[2] = {0, 0}, ul[2] = {0, 0};
@@ -655,13 +684,14 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
         }
         if (pr < npairs) {
             const int valid0 = (int)len - 4 * k;
+            nz |= valid0 >= 8 ? (x[0] | x[1]) : ((x[0] & tail_mask(valid0)) | (x[1] & tail_mask(valid0 - 4)));
 #pragma unroll
             for (int i = 0; i < 2; i++) {
                 const int valid = valid0 - 4 * i;
                 if (valid <= 0) break;
                 const uint32_t xp = i ? x[0] : xprev;
-                if (valid >= 4) dense_word0(prmt(x[i], 0u, rt), prmt(x[i], xp, rp), dense_base, c1, c2);
-                else dense_word0_slow(x[i], xp, valid, dense_base, rep);
+                if (valid >= 4) dense_word0(prmt(x[i], 0u, rt), prmt(x[i], xp, rp), dense_base);
+                else dense_word0_slow(x[i], xp, valid, dense_base);
 #pragma unroll
                 for (int f = 0; f < 4; f++) {
                     const uint32_t tp = i ? t[f][0] : tprev[f];
@@ -682,13 +712,15 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
         }
     }
     __syncthreads();
+    // every warp is past the previous row's write pass: with a 3-slot ring the oldest slot may be refilled from here on
+    issue_prefetch<NT>(pf);
     // sweep the dense tables (sum of the two replicas), four keys at a time, and the outlier hashes
     {
         uint4 *dn = reinterpret_cast<uint4 *>(sm.small);
-        // q < 1024: trial-1 : 2 | first : 5 | group of four seconds : 3;  q >= 1024: trial 0, first : 5 | group : 3
-        for (uint32_t q = threadIdx.x; q < 1280u; q += NT) {
-            const uint32_t f = q < 1024u ? 1u + (q >> 8) : 0u, first = (q >> 3) & 31u, g = q & 7u;
-            uint4 *c0 = dn + (f ? first * 64u + (f - 1u) * 16u : 2048u + first * 16u) + g, *c1 = c0 - g + 8u + (g ^ 4u);
+        // trials 1..4: q = trial-1 : 2 | first : 5 | group of four seconds : 3
+        for (uint32_t q = threadIdx.x; q < 1024u; q += NT) {
+            const uint32_t f = 1u + (q >> 8), first = (q >> 3) & 31u, g = q & 7u;
+            uint4 *c0 = dn + first * 64u + (f - 1u) * 16u + g, *c1 = c0 - g + 8u + (g ^ 4u);
             const uint4 a = *c0, b = *c1;
             *c0 = make_uint4(0, 0, 0, 0);
             *c1 = make_uint4(0, 0, 0, 0);
@@ -698,7 +730,7 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
             // the trial's outlier hash table (HSLOTS / 4 cells, one per thread of the trial's first 128): counted unless
             // the trial is flagged (then only cleared)
             const uint32_t w = q & 255u;
-            if (f && w < HSLOTS / 4) {
+            if (w < HSLOTS / 4) {
                 uint4 *cell = reinterpret_cast<uint4 *>(sm.ohash + (f - 1) * HSLOTS) + w;
                 const uint4 v = *cell;
                 if (v.x | v.y | v.z | v.w) {
@@ -719,10 +751,27 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
                 atomicAdd(&sm.s_bge_()[f], e);
             }
         }
+        // trial 0 (coarse keys): 1024 counters, four per step
+        {
+            uint4 *d4 = reinterpret_cast<uint4 *>(sm.small) + 2048u;
+            uint32_t d = 0, e = 0;
+            for (uint32_t q = threadIdx.x; q < 256u; q += NT) {
+                const uint4 a = d4[q];
+                d4[q] = make_uint4(0, 0, 0, 0);
+                d += (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0);
+                e += ilog2i_z(a.x) + ilog2i_z(a.y) + ilog2i_z(a.z) + ilog2i_z(a.w);
+            }
+            d = warp_sum(d);
+            e = warp_sum(e);
+            if (lane == 0 && d) {
+                atomicAdd(&sm.s_bgc_()[0], d);
+                atomicAdd(&sm.s_bge_()[0], e);
+            }
+        }
     }
     // flagged trials: their outlier windows, re-derived from the staged row, are counted in h0, one trial at a time
     const uint32_t flagged = sm.s_out_()[1] | sm.s_out_()[2] << 1 | sm.s_out_()[3] << 2 | sm.s_out_()[4] << 3; // uniform
-    if (flagged == 0) return;
+    if (flagged == 0) return nz;
     __syncthreads(); // h0 is clean
     for (int f = 1; f < 5; f++) {
         if (!((flagged >> (f - 1)) & 1u)) continue;
@@ -742,6 +791,7 @@ __device__ __forceinline__ void bigram_row_small(const uint8_t *cur, const uint8
         }
         __syncthreads();
     }
+    return nz;
 }
 
 // ---- writing the chosen row --------------------------------------------------------------------------------------
@@ -804,9 +854,47 @@ __device__ __forceinline__ void coop_load_row(uint8_t *dst, const uint8_t *src, 
     }
 }
 
+// The filter a strategy uses for one row (png/mod.rs:385-421): fixed for Basic / Predefined; for the heuristics the
+// winner of the five trials under the reference's strict comparisons in RowFilter::ALL order (lowest id wins ties),
+// None for all-zero rows.  `exact0`: the exact Bigrams/BigEnt scores of trial 0 are in slot 5 (bigram_exact0).
+__device__ __forceinline__ int decide_row(const DevStrategy &st, uint32_t r, uint32_t len, const Smem &sr, bool heur, bool exact0) {
+    int f = 0;
+    if (st.kind == OXI_BASIC) {
+        f = st.basic;
+    } else if (st.kind == OXI_PREDEFINED) {
+        f = r < st.n_predefined ? st.predefined[r] : 0; // png/mod.rs:389
+    } else if (heur) {
+        if (st.kind == OXI_MINSUM) { // smaller is better, strict '<' (strategies.rs:95)
+            uint32_t best = 0xFFFFFFFFu;
+            const uint32_t nbytes = 16 * ((len + 15) >> 4);
+#pragma unroll
+            for (int q = 0; q < 5; q++) {
+                const uint32_t s = 128u * nbytes - sr.s_min_()[q] + (uint32_t)q;
+                if (s < best || q == 0) { best = s; f = q; }
+            }
+        } else if (st.kind == OXI_BIGRAMS) { // fewer distinct bigrams, strict '<' (strategies.rs:182-189)
+            uint32_t best = 0;
+#pragma unroll
+            for (int q = 0; q < 5; q++) {
+                const uint32_t s = sr.s_bgc_()[q == 0 && exact0 ? 5 : q];
+                if (q == 0 || s < best) { best = s; f = q; }
+            }
+        } else { // Entropy / BigEnt: larger is better, strict '>' on i32 (strategies.rs:143,221)
+            const uint32_t *sc = st.kind == OXI_ENTROPY ? sr.s_ent_() : sr.s_bge_();
+            int32_t best = 0;
+#pragma unroll
+            for (int q = 0; q < 5; q++) {
+                const int32_t s = (int32_t)sc[q == 0 && exact0 && st.kind == OXI_BIGENT ? 5 : q];
+                if (q == 0 || s > best) { best = s; f = q; }
+            }
+        }
+    }
+    return f;
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 template <int D, int SC>
-__global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC_BIGRAM) ? 1 : (SC == SC_MINSUM || SC == 0) ? 3 : 2) k_fast(const __grid_constant__ FastParams P) {
+__global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (SC & SC_BIGRAM) ? 1 : (SC == SC_MINSUM || SC == 0) ? 3 : 2) k_fast(const __grid_constant__ FastParams P) {
     constexpr int NT = threads_for(SC);
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t NS = P.nslot;
@@ -832,7 +920,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
     __syncthreads();
 
     uint32_t parity = 0;  // bit s = phase to wait for on slot s
-    uint32_t row_ctr = 0; // rows scored by this CTA so far: selects the score set
+    uint32_t set_cur = 0; // score set of the next scored row (three sets rotate)
     const uint64_t total_items = P.n_images * (uint64_t)P.items_per_image;
     bool any_heur = false, want_bg = false, want_be = false;
     for (int j = 0; j < P.set.k; j++) {
@@ -842,7 +930,8 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
     }
     // With a 4-slot ring a slot is refilled two iterations after its last reader, and every scored row contains at
     // least one CTA-wide barrier, so the end-of-row barrier is only needed for the 3-slot ring / unscored rows.
-    const bool row_end_barrier = NS < 4 || SC == 0 || !any_heur;
+    const bool defer_pf = (SC & SC_BIGRAM) && ((SC & SC_HALF) || P.small_tab) && any_heur && NS < 4;
+    const bool row_end_barrier = (NS < 4 && !defer_pf) || SC == 0 || !any_heur;
 
     for (uint64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
         const uint64_t img = item / P.items_per_image;
@@ -857,6 +946,11 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
         if (k0 >= k1) continue;
         const uint32_t len = pd.len;
         const uint8_t *src0 = P.data + img * P.g.data_len + pd.in_base; // first row of the pass
+        // row k of the pass starts at band_off + k * (len + 1) of a strategy's output (in_base + k*len bytes of earlier
+        // rows of the image plus one filter byte per earlier row) and is row used_off + k of its filters_used
+        const uint64_t band_off = img * P.g.out_len + pd.in_base + pd.row0;
+        const uint64_t used_off = img * P.g.total_rows + pd.row0;
+        const uint32_t g32 = (((len + 16) >> 4) + 31) & ~31u; // 16-byte granules of an output row, in whole warps
         const bool tma = ((reinterpret_cast<uintptr_t>(src0) | len) & 15u) == 0;
 
         // prologue: previous row (or zeros at a pass start, png/mod.rs:375-378) into slot 0, first row into slot 1
@@ -888,16 +982,18 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
         for (uint32_t k = k0; k < k1; k++) {
             const uint8_t *cur = sm.rows + sc_ * (size_t)P.rb + PAD;
             const uint8_t *up = sm.rows + sp * (size_t)P.rb + PAD;
-            if (k + 1 < k1) { // stream the next row in behind the current one
-                uint8_t *dst = sm.rows + sn * (size_t)P.rb + PAD;
-                if (tma) {
-                    if (tid == 0) {
-                        mbar_expect_tx(&sm.bar[sn], len);
-                        tma_load_1d(dst, src0 + (size_t)(k + 1) * len, len, &sm.bar[sn]);
-                    }
-                } else {
-                    coop_load_row<NT>(dst, src0 + (size_t)(k + 1) * len, len);
-                }
+            // stream the next row in behind the current one: here, or (3-slot ring, small-table bigram scorer) behind the
+            // scorer's first barrier, which makes the end-of-row barrier unnecessary
+            Prefetch pf;
+            pf.on = k + 1 < k1;
+            pf.tma = tma;
+            pf.dst = sm.rows + sn * (size_t)P.rb + PAD;
+            pf.src = src0 + (size_t)(k + 1) * len;
+            pf.len = len;
+            pf.bar = &sm.bar[sn];
+            if (!defer_pf) {
+                issue_prefetch<NT>(pf);
+                pf.on = false;
             }
             if (tma) {
                 mbar_wait(&sm.bar[sc_], (parity >> sc_) & 1u);
@@ -905,15 +1001,18 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
             }
 
             const uint32_t r = pd.row0 + k;
-            const uint64_t in_off = pd.in_base + (uint64_t)k * len;
-            bool heur = false, need0 = false;
+            const uint64_t row_off = band_off + (uint64_t)k * (len + 1u); // of this row in a strategy's filtered stream
+            bool heur = false, need0 = false, decided = false;
             // score set of this row; the set of the row after next is cleared here, before this row's barriers:
             // its last readers (decisions two rows ago) are behind the previous row's barriers
             Smem sr = sm;
-            sr.sc = sm.sc + (row_ctr % 3u) * SCORE_WORDS;
+            sr.sc = sm.sc + set_cur * SCORE_WORDS;
+            const uint32_t set_next = set_cur == 2u ? 0u : set_cur + 1u;
+            uint8_t *fsel = reinterpret_cast<uint8_t *>(sr.s_min_() + 5); // 12 bytes: the filter chosen per strategy
             if (SC != 0 && any_heur) {
-                if (tid < (int)SCORE_WORDS) sm.sc[((row_ctr + 1u) % 3u) * SCORE_WORDS + tid] = 0;
+                if (tid < (int)SCORE_WORDS) sm.sc[set_next * SCORE_WORDS + tid] = 0;
                 uint32_t nz = 0;
+                bool small_flow = false;
                 if (SC & SC_MINSUM) nz = minsum_pass<D, NT>(cur, up, len, shift, sr.s_min_());
                 if (SC & SC_ENTROPY) {
                     entropy_pass<D, NT>(cur, up, len, shift, sm.hist);
@@ -922,77 +1021,80 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? 2 : (SC & SC
                 }
                 if (SC & SC_BIGRAM) {
                     const uint32_t wpt = (((len + 3) >> 2) + NT - 1) / NT; // row words per thread
-                    if ((SC & SC_HALF) || P.small_tab) bigram_row_small<D, NT>(cur, up, len, shift, bpp, sr, P.h0_slots);
+                    if ((SC & SC_HALF) || P.small_tab) {
+                        nz |= bigram_row_small<D, NT>(cur, up, len, shift, bpp, sr, P.h0_slots, pf);
+                        small_flow = true;
+                    }
                     else if (wpt <= 1) bigram_row<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
                     else if (wpt <= 2) bigram_row<D, NT, 2>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
                     else if (wpt <= 4) bigram_row<D, NT, 4>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
                     else bigram_row<D, NT, 8>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
                 }
-                // all-zero rows short-circuit to None (png/mod.rs:398-404); decided at the scorers' last barrier
-                // (the MinSum sweep has already OR-ed the row)
-                const uint4 *c4 = reinterpret_cast<const uint4 *>(cur);
-                const uint32_t nchunks = (SC & SC_MINSUM) ? 0u : (len + 15) >> 4;
-                for (uint32_t c = tid; c < nchunks; c += NT) {
-                    uint4 v = c4[c];
-                    const int valid = (int)len - (int)(16 * c);
-                    if (valid < 16) {
-                        v.x &= tail_mask(valid); v.y &= tail_mask(valid - 4); v.z &= tail_mask(valid - 8);
-                        v.w &= tail_mask(valid - 12);
+                if ((SC & SC_BIGRAM) && small_flow) {
+                    // Every warp has added its scores; the warp that arrives last decides for all strategies before
+                    // the CTA-wide barrier, the others only read its choices behind the barrier.  The arrival counter
+                    // (s_out[0]) carries "some byte of the row is non-zero" in its upper half.
+                    const bool wnz = __any_sync(0xffffffffu, nz != 0);
+                    uint32_t arrived = 0;
+                    if ((tid & 31) == 0) {
+                        __threadfence_block();
+                        arrived = atomicAdd(&sr.s_out_()[0], 1u | (wnz ? 0x10000u : 0u)) + (1u | (wnz ? 0x10000u : 0u));
                     }
-                    nz |= v.x | v.y | v.z | v.w;
+                    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+                    if ((arrived & 0xFFFFu) == NT / 32) {
+                        __threadfence_block();
+                        const bool hz = (arrived >> 16) != 0;
+                        bool n0 = false;
+                        if (hz) {
+                            // scores 0 are the coarse bounds of trial 0 (bigram_row_small); the exact pass runs only
+                            // when they leave open that None wins (it wins ties: d0 <= min d_f, e0 >= max e_f)
+                            const volatile uint32_t *bc = sr.s_bgc_(), *be = sr.s_bge_();
+                            const uint32_t dmin = min(min(bc[1], bc[2]), min(bc[3], bc[4]));
+                            const int32_t emax = max(max((int32_t)be[1], (int32_t)be[2]), max((int32_t)be[3], (int32_t)be[4]));
+                            n0 = (want_bg && bc[0] <= dmin) || (want_be && (int32_t)be[0] >= emax);
+                        }
+                        const int j = tid & 31;
+                        if (j < P.set.k && !n0) fsel[j] = (uint8_t)decide_row(P.set.s[j], r, len, sr, hz, false);
+                        if (j == 0) sr.s_out_()[5] = (hz ? 1u : 0u) | (n0 ? 2u : 0u);
+                    }
+                    __syncthreads();
+                    const uint32_t fl = sr.s_out_()[5];
+                    heur = (fl & 1u) != 0;
+                    need0 = (fl & 2u) != 0;
+                    if (need0) {
+                        bigram_exact0<NT>(cur, len, sm.table, P.h0_slots, sr.s_bgc_(), sr.s_bge_());
+                        if (tid < P.set.k) fsel[tid] = (uint8_t)decide_row(P.set.s[tid], r, len, sr, true, true);
+                        __syncthreads();
+                    }
+                    decided = true;
+                } else {
+                    // all-zero rows short-circuit to None (png/mod.rs:398-404); decided at the scorers' last barrier
+                    // (the MinSum sweep has already OR-ed the row)
+                    const uint4 *c4 = reinterpret_cast<const uint4 *>(cur);
+                    const uint32_t nchunks = (SC & SC_MINSUM) ? 0u : (len + 15) >> 4;
+                    for (uint32_t c = tid; c < nchunks; c += NT) {
+                        uint4 v = c4[c];
+                        const int valid = (int)len - (int)(16 * c);
+                        if (valid < 16) {
+                            v.x &= tail_mask(valid); v.y &= tail_mask(valid - 4); v.z &= tail_mask(valid - 8);
+                            v.w &= tail_mask(valid - 12);
+                        }
+                        nz |= v.x | v.y | v.z | v.w;
+                    }
+                    heur = __syncthreads_or(nz != 0) != 0;
                 }
-                heur = __syncthreads_or(nz != 0) != 0;
-                row_ctr++;
-                if ((SC & SC_BIGRAM) && P.small_tab && heur) {
-                    // scores 0 are the coarse bounds of trial 0 (bigram_row_small); the exact pass runs only when they
-                    // leave open that None wins (it wins ties: d0 <= min d_f, e0 >= max e_f)
-                    const uint32_t *bc = sr.s_bgc_(), *be = sr.s_bge_();
-                    const uint32_t dmin = min(min(bc[1], bc[2]), min(bc[3], bc[4]));
-                    const int32_t emax = max(max((int32_t)be[1], (int32_t)be[2]), max((int32_t)be[3], (int32_t)be[4]));
-                    need0 = (want_bg && bc[0] <= dmin) || (want_be && (int32_t)be[0] >= emax);
-                    if (need0) bigram_exact0<NT>(cur, len, sm.table, P.h0_slots, sr.s_bgc_(), sr.s_bge_());
-                }
+                set_cur = set_next;
             }
 
             for (int j2 = 0; j2 < P.set.k; j2++) {
                 const DevStrategy &st = P.set.s[j2];
                 // the write pass of strategy j2 runs on the warps starting at `rot`; the others have nothing to do for
                 // it (a row has (len+16)/16 granules plus <= 31 edge bytes) and skip the decision as well
-                const int rot = (int)((j2 * ((((len + 16) >> 4) + 31) & ~31u)) & (NT - 1));
-                if ((int)(((int)threadIdx.x - rot) & (NT - 1)) >= (int)((((len + 16) >> 4) + 31) & ~31u) + 32) continue;
-                int f = 0;
-                if (st.kind == OXI_BASIC) {
-                    f = st.basic;
-                } else if (st.kind == OXI_PREDEFINED) {
-                    f = r < st.n_predefined ? st.predefined[r] : 0; // png/mod.rs:389
-                } else if (heur) {
-                    if (st.kind == OXI_MINSUM) { // smaller is better, strict '<' (strategies.rs:95)
-                        uint32_t best = 0xFFFFFFFFu;
-                        const uint32_t nbytes = 16 * ((len + 15) >> 4);
-#pragma unroll
-                        for (int q = 0; q < 5; q++) {
-                            const uint32_t s = 128u * nbytes - sr.s_min_()[q] + (uint32_t)q;
-                            if (s < best || q == 0) { best = s; f = q; }
-                        }
-                    } else if (st.kind == OXI_BIGRAMS) { // fewer distinct bigrams, strict '<' (strategies.rs:182-189)
-                        uint32_t best = 0;
-#pragma unroll
-                        for (int q = 0; q < 5; q++) {
-                            const uint32_t s = sr.s_bgc_()[q == 0 && need0 ? 5 : q];
-                            if (q == 0 || s < best) { best = s; f = q; }
-                        }
-                    } else { // Entropy / BigEnt: larger is better, strict '>' on i32 (strategies.rs:143,221)
-                        const uint32_t *sc = st.kind == OXI_ENTROPY ? sr.s_ent_() : sr.s_bge_();
-                        int32_t best = 0;
-#pragma unroll
-                        for (int q = 0; q < 5; q++) {
-                            const int32_t s = (int32_t)sc[q == 0 && need0 && st.kind == OXI_BIGENT ? 5 : q];
-                            if (q == 0 || s > best) { best = s; f = q; }
-                        }
-                    }
-                }
-                write_row<NT>(f, cur, up, len, bpp, st.out + img * P.g.out_len + in_off + r, rot);
-                if (tid == rot) st.filters_used[img * P.g.total_rows + r] = (uint8_t)f;
+                const int rot = (int)((j2 * g32) & (NT - 1));
+                if ((int)(((int)threadIdx.x - rot) & (NT - 1)) >= (int)g32 + 32) continue;
+                const int f = decided ? (int)fsel[j2] : decide_row(st, r, len, sr, heur, false);
+                write_row<NT>(f, cur, up, len, bpp, st.out + row_off, rot);
+                if (tid == rot) st.filters_used[used_off + k] = (uint8_t)f;
             }
             if (row_end_barrier) __syncthreads(); // slot `sp` may be refilled by the next iteration's prefetch
             sp = sc_;
@@ -1069,8 +1171,8 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
     P.h0_slots = P.small_tab ? h0 : 0;
     // ... and with rows <= 4096 bytes two 512-thread CTAs fit an SM (two rows in flight: one CTA's barriers and table
     // sweeps overlap the other's counting)
-    const uint32_t two_per_sm = (233472u / 2 - 1024u) & ~127u;
-    if (sc == SC_BIGRAM && P.small_tab && g.max_len <= 4096 && smem_bytes_for(sc, P.rb, h0, 3) <= two_per_sm) sc |= SC_HALF;
+    const uint32_t two_per_sm = (233472u / HALF_OCC - 1024u) & ~127u; // shared memory of one of HALF_OCC resident CTAs
+    if (sc == SC_BIGRAM && P.small_tab && g.max_len <= 4096 && smem_bytes_for(sc | SC_HALF, P.rb, h0, 3) <= two_per_sm) sc |= SC_HALF;
     const int nt = threads_for(sc);
     // a fourth ring slot removes the end-of-row barrier; take it when it does not cost occupancy (rows <= 16 KB)
     const uint32_t budget = (sc & SC_HALF) ? two_per_sm : SMEM_LIMIT;
@@ -1099,7 +1201,8 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
     // multiple of the resident CTA slots instead (every CTA gets the same number of near-equal bands).
     const uint64_t slots = (uint64_t)ctx.num_sms * occ;
     const uint64_t rows_total = (uint64_t)n_images * g.total_rows;
-    const uint32_t R = (sc & (SC_BIGRAM | SC_ENTROPY)) ? 8 : 32;
+    uint32_t R = (sc & (SC_BIGRAM | SC_ENTROPY)) ? 8 : 32;
+    if (rows_total / 32 >= 24 * slots) R = 32; // plenty of bands either way: fewer band prologues
     uint64_t want_items = (rows_total + R - 1) / R;
     if (want_items < 6 * slots) {
         uint64_t waves = want_items / slots;

@@ -179,6 +179,46 @@ def test_bigram_outlier_paths():
                        strategies=["None", "Bigrams", "BigEnt"], label=f"spikes-o4/{w}x{h}/{spikes}/{hot}")
 
 
+def test_bigram_none_trial_bounds_and_exact_pass():
+    """The fast bigram scorer scores the None trial on coarse keys (low five bits) and reruns it exactly only when the
+    bounds leave open that None wins.  Rows built so that None wins, ties, or loses narrowly: few-valued rows (graphics),
+    rows whose values differ only above bit 4 (coarse keys collide, exact keys do not), constant rows, and rows where
+    Sub/Up are as good as None."""
+    import oxipng_b200 as ox
+    rng = np.random.default_rng(4242)
+    for (w, h, ct) in [(1024, 24, 6), (333, 17, 2), (2048, 9, 0)]:
+        ch = {0: 1, 2: 3, 6: 4}[ct]
+        L = w * ch
+        rows = []
+        for y in range(h):
+            kind = y % 8
+            if kind == 0:      # two-valued stripes: None has very few bigrams
+                r = np.where((np.arange(L) // (3 + y)) % 2 == 0, 17, 201)
+            elif kind == 1:    # values that differ only in the high bits: coarse keys merge, exact keys do not
+                r = 5 + 32 * rng.integers(0, 8, size=L)
+            elif kind == 2:    # constant row
+                r = np.full(L, 90 + y)
+            elif kind == 3:    # equal to the row above (Up gives zeros), None still cheap
+                r = rows[-1].copy()
+            elif kind == 4:    # small alphabet, random order
+                r = rng.choice(np.array([0, 1, 2, 64, 65, 130]), size=L)
+            elif kind == 5:    # period-bpp pattern: Sub gives zeros after the first pixel
+                r = np.tile(np.array([10, 60, 110, 160, 210, 5, 100, 200])[:ch], w)
+            elif kind == 6:    # noise: every trial is bad, None's bounds are loose
+                r = rng.integers(0, 256, size=L)
+            else:              # smooth ramp
+                r = (np.arange(L) // ch) // 5 + 3 * (np.arange(L) % ch)
+            rows.append(np.asarray(r, dtype=np.int64) & 0xFF)
+        a = np.stack(rows).astype(np.uint8)
+        ih = (w, h, ct, 8, 0)
+        _check(ih, a.tobytes(), alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["Bigrams", "BigEnt"],
+               label=f"none-bounds/{w}x{h}/{ct}")
+        _check(ih, a.tobytes(), alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["BigEnt"], label="none-bounds-be")
+        _check(ih, a.tobytes(), alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["Bigrams"], label="none-bounds-bg")
+        _check(ih, a.tobytes(), alphas=(False,), flags=ox.FLAG_FORCE_FAST,
+               strategies=["MinSum", "Entropy", "Bigrams", "BigEnt"], label="none-bounds-all")
+
+
 def test_fast_tier_batch_many_images():
     import oxipng_b200 as ox
     n = 37

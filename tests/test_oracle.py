@@ -19,6 +19,21 @@ from pngload import load_png, to_samples, write_png
 HAVE_REF = os.path.isdir(helpers.REF_FILES)
 
 
+def test_ilog2i_is_superadditive():
+    """The CUDA bigram scorer bounds the None trial on coarsened keys (oxipng_b200/csrc/filter_fast.cu,
+    bigram_row_small): merging two keys must never lower sum ilog2i(count).  ilog2i is piecewise linear with slopes
+    lg+2 that grow with i and ilog2i(0) := 0, i.e. convex through the origin, hence superadditive -- checked here."""
+    f = oracle.lib().oxo_ilog2i
+    g = [0] + [f(i) for i in range(1, 8200)]
+    slopes = [g[i + 1] - g[i] for i in range(len(g) - 1)]
+    assert all(a <= b for a, b in zip(slopes, slopes[1:]))
+    import random
+    rnd = random.Random(5)
+    for _ in range(20000):
+        a, b = rnd.randint(1, 4096), rnd.randint(1, 4096)
+        assert g[a + b] >= g[a] + g[b]
+
+
 def test_ilog2i_known_values():
     # strategies.rs:269-272: i*floor(log2 i) + 2*(i - 2^floor(log2 i))
     assert [oracle.lib().oxo_ilog2i(i) for i in range(1, 9)] == [0, 2, 5, 8, 12, 16, 20, 24]
