@@ -220,34 +220,37 @@ __host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, uint32_t h0_slots, 
 // MinSum for all five filters in one sweep. Accumulates S_f = sum over bytes of ||cur-pred_f| - 128|; the caller turns
 // it into the reference's score 128*bytes - S_f + f (the filter-type byte f counts |f| = f, png/mod.rs:409-414).
 // Returns the OR of this thread's row words (for the all-zero-row test, so that no separate scan is needed).
+template <int D, bool TAIL>
+__device__ __forceinline__ void minsum_chunk(const uint8_t *cur, const uint8_t *up, uint32_t c, int valid, uint32_t shift,
+                                             uint32_t (&a)[5], uint32_t &nz) {
+    const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
+    const uint32_t H = 0x80808080u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t x = cw.w[k + 2], u = uw.w[k + 2], l = left_word<D>(cw, k, shift), ul = left_word<D>(uw, k, shift);
+        if (TAIL) { // last, partial chunk: bytes past the row contribute |0-0| -> cancel exactly
+            const uint32_t m = tail_mask(valid - 4 * k);
+            x &= m; u &= m; l &= m; ul &= m;
+        }
+        nz |= x;
+        a[0] = __vsadu4(x, H) + a[0];
+        a[1] = __vsadu4(__vabsdiffu4(x, l), H) + a[1];
+        a[2] = __vsadu4(__vabsdiffu4(x, u), H) + a[2];
+        a[3] = __vsadu4(__vabsdiffu4(x, __vhaddu4(l, u)), H) + a[3];
+        a[4] = __vsadu4(__vabsdiffu4(x, paeth4(l, u, ul)), H) + a[4];
+    }
+}
 template <int D, int NT>
 __device__ __forceinline__ uint32_t minsum_pass(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
                                                 uint32_t *s_min) {
-    const uint32_t nchunks = (len + 15) >> 4;
-    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, nz = 0;
-    const uint32_t H = 0x80808080u;
-    for (uint32_t c = threadIdx.x; c < nchunks; c += NT) {
-        const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
-        const int valid = (int)len - (int)(16 * c);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t x = cw.w[k + 2], u = uw.w[k + 2], l = left_word<D>(cw, k, shift), ul = left_word<D>(uw, k, shift);
-            if (valid < 16) { // last, partial chunk: bytes past the row contribute |0-0| -> cancel exactly
-                const uint32_t m = tail_mask(valid - 4 * k);
-                x &= m; u &= m; l &= m; ul &= m;
-            }
-            nz |= x;
-            a0 = __vsadu4(x, H) + a0;
-            a1 = __vsadu4(__vabsdiffu4(x, l), H) + a1;
-            a2 = __vsadu4(__vabsdiffu4(x, u), H) + a2;
-            a3 = __vsadu4(__vabsdiffu4(x, __vhaddu4(l, u)), H) + a3;
-            a4 = __vsadu4(__vabsdiffu4(x, paeth4(l, u, ul)), H) + a4;
-        }
-    }
-    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4);
+    const uint32_t nfull = len >> 4; // complete 16-byte chunks: no masking in the main loop
+    uint32_t a[5] = {0, 0, 0, 0, 0}, nz = 0;
+    for (uint32_t c = threadIdx.x; c < nfull; c += NT) minsum_chunk<D, false>(cur, up, c, 16, shift, a, nz);
+    if ((len & 15u) && threadIdx.x == (nfull % NT)) minsum_chunk<D, true>(cur, up, nfull, (int)(len & 15u), shift, a, nz);
+    a[0] = warp_sum(a[0]); a[1] = warp_sum(a[1]); a[2] = warp_sum(a[2]); a[3] = warp_sum(a[3]); a[4] = warp_sum(a[4]);
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&s_min[0], a0); atomicAdd(&s_min[1], a1); atomicAdd(&s_min[2], a2);
-        atomicAdd(&s_min[3], a3); atomicAdd(&s_min[4], a4);
+        atomicAdd(&s_min[0], a[0]); atomicAdd(&s_min[1], a[1]); atomicAdd(&s_min[2], a[2]);
+        atomicAdd(&s_min[3], a[3]); atomicAdd(&s_min[4], a[4]);
     }
     return nz;
 }
