@@ -51,7 +51,7 @@ struct FastParams {
     uint32_t small_tab; // bigram scorer: five dense 64x64 in-range tables are carved (rows <= 8192 bytes)
 };
 
-__host__ __device__ constexpr int threads_for(int sc) { return (sc & SC_HALF) ? HALF_NT : (sc & SC_BIGRAM) ? 1024 : 256; }
+__host__ __device__ constexpr int threads_for(int sc) { return (sc & SC_HALF) ? HALF_NT : (sc & SC_BIGRAM) ? 1024 : sc == SC_ENTROPY ? 512 : 256; }
 
 // ---- PTX wrappers: mbarrier + 1-D bulk tensor-memory-accelerator copy -----------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,6 +80,14 @@ __device__ __forceinline__ uint32_t signmask4(uint32_t x) { // 0xFF in every byt
     uint32_t d;                                             // (prmt's sign-replicate selectors; __byte_perm masks them off)
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xba98u));
     return d;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { // full prmt (sign-replicate nibbles kept)
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ void smem_inc(uint32_t addr) { // no-return add of 1 on a shared-window byte address
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
 }
 __device__ __forceinline__ uint32_t sel4(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
 
@@ -183,9 +191,9 @@ struct Smem {
     uint32_t *ohash;   // [4][HSLOTS] outlier bigrams of trials 1..4: open-addressing tables of (key << 16 | count)
 };
 constexpr uint32_t SMALL_BYTES = DENSE_WORDS * 4 + 4 * HSLOTS * 4; // dense tables + outlier hashes
-// h0_slots != 0 selects the small-table layout: header | dense tables | outlier hashes | h0 | row ring | histograms.
+// h0_slots != 0 selects the small-table layout: header | histograms | dense tables | outlier hashes | h0 | row ring.
 // The tables come first so that their shared-memory offsets are compile-time constants (immediates of the atomics).
-// Otherwise: header | row ring | histograms | 65536-entry bigram table.
+// Otherwise: header | histograms | row ring | 65536-entry bigram table.
 template <int SC>
 __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot, uint32_t h0_slots) {
     Smem s;
@@ -193,6 +201,8 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot
     uint32_t *u = reinterpret_cast<uint32_t *>(base + 64);
     s.sc = u; // set 0; sets 1 and 2 follow at SCORE_WORDS strides
     uint8_t *p = base + SMEM_HDR;
+    s.hist = reinterpret_cast<uint32_t *>(p); // histograms first: fixed offset, immediates of the atomics
+    if (SC & SC_ENTROPY) p += 5 * HIST_REP * 256 * 4;
     s.small = reinterpret_cast<uint32_t *>(p);
     s.ohash = s.small + DENSE_WORDS;
     s.table = s.ohash + 4 * HSLOTS;
@@ -202,8 +212,6 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot
     if (SC & SC_HALF) s.table = s.small;
     s.rows = p;
     p += nslot * (size_t)rb;
-    s.hist = reinterpret_cast<uint32_t *>(p);
-    if (SC & SC_ENTROPY) p += 5 * HIST_REP * 256 * 4;
     if (!((SC & SC_BIGRAM) && h0_slots)) s.table = reinterpret_cast<uint32_t *>(p);
     return s;
 }
@@ -255,41 +263,54 @@ __device__ __forceinline__ uint32_t minsum_pass(const uint8_t *cur, const uint8_
     return nz;
 }
 
-__device__ __forceinline__ void hist_add4(uint32_t *h, uint32_t r, int nvalid) {
-    if (nvalid >= 4) {
-        atomicAdd(h + (r & 255u), 1u);
-        atomicAdd(h + ((r >> 8) & 255u), 1u);
-        atomicAdd(h + ((r >> 16) & 255u), 1u);
-        atomicAdd(h + (r >> 24), 1u);
-    } else {
-        for (int j = 0; j < nvalid; j++) atomicAdd(h + ((r >> (8 * j)) & 255u), 1u);
+// Entropy: histogram the residual bytes of all five filters (filter-type byte added at scoring time).  The counter of
+// byte value v of filter f in the lane's replica rep sits at byte offset f*4096 + rep*1024 + (v ^ 8*rep)*4 (the
+// rotation spreads the replicas of one hot value over the banks): low byte (v & 63) << 2, high byte v >> 6 | rep << 2,
+// composed per window by one prmt out of two pre-scaled words; f*4096 is an immediate of the atomic.
+__device__ __forceinline__ void hist_word(uint32_t hist_base, uint32_t r, uint32_t rotw, uint32_t crep) {
+    const uint32_t rx = r ^ rotw;
+    const uint32_t lo = (rx * 4u) & 0xFCFCFCFCu, hi = ((rx >> 6) & 0x03030303u) | crep;
+    smem_inc(hist_base + prmt(lo, hi, 0xCC40u));
+    smem_inc(hist_base + prmt(lo, hi, 0xDD51u));
+    smem_inc(hist_base + prmt(lo, hi, 0xEE62u));
+    smem_inc(hist_base + prmt(lo, hi, 0xFF73u));
+}
+__device__ __forceinline__ void hist_word_tail(uint32_t hist_base, uint32_t r, uint32_t rep, int nvalid) {
+    for (int j = 0; j < nvalid; j++) smem_inc(hist_base + rep * 1024u + ((((r >> (8 * j)) & 255u) ^ (8u * rep)) << 2));
+}
+template <int D, bool TAIL>
+__device__ __forceinline__ void entropy_chunk(const uint8_t *cur, const uint8_t *up, uint32_t c, int valid, uint32_t shift,
+                                              uint32_t hist_base, uint32_t rep) {
+    const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
+    const uint32_t rotw = rep * 0x08080808u, crep = rep * 0x04040404u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t x = cw.w[k + 2], u = uw.w[k + 2], l = left_word<D>(cw, k, shift), ul = left_word<D>(uw, k, shift);
+        const uint32_t r1 = __vsub4(x, l), r2 = __vsub4(x, u), r3 = __vsub4(x, __vhaddu4(l, u)), r4 = __vsub4(x, paeth4(l, u, ul));
+        if (!TAIL) {
+            hist_word(hist_base + 0 * 4096u, x, rotw, crep);
+            hist_word(hist_base + 1 * 4096u, r1, rotw, crep);
+            hist_word(hist_base + 2 * 4096u, r2, rotw, crep);
+            hist_word(hist_base + 3 * 4096u, r3, rotw, crep);
+            hist_word(hist_base + 4 * 4096u, r4, rotw, crep);
+        } else {
+            const int nv = min(valid - 4 * k, 4);
+            if (nv <= 0) break;
+            hist_word_tail(hist_base + 0 * 4096u, x, rep, nv);
+            hist_word_tail(hist_base + 1 * 4096u, r1, rep, nv);
+            hist_word_tail(hist_base + 2 * 4096u, r2, rep, nv);
+            hist_word_tail(hist_base + 3 * 4096u, r3, rep, nv);
+            hist_word_tail(hist_base + 4 * 4096u, r4, rep, nv);
+        }
     }
 }
-
-// Entropy: histogram the residual bytes of all five filters (filter-type byte added at scoring time).
 template <int D, int NT>
 __device__ __forceinline__ void entropy_pass(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
                                              uint32_t *hist) {
-    const uint32_t nchunks = (len + 15) >> 4;
-    // replica by lane; the bins of replica k are stored at bin ^ 8k: the replicas' bases are multiples of 256 words, so
-    // without the rotation the copies of one hot bin would all sit in the same bank
-    const uint32_t rep = threadIdx.x & (HIST_REP - 1), rotw = rep * 0x08080808u;
-    uint32_t *h = hist + rep * 256;
-    for (uint32_t c = threadIdx.x; c < nchunks; c += NT) {
-        const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
-        const int valid = (int)len - (int)(16 * c);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t x = cw.w[k + 2], u = uw.w[k + 2], l = left_word<D>(cw, k, shift), ul = left_word<D>(uw, k, shift);
-            const int nv = valid - 4 * k;
-            if (nv <= 0) break;
-            hist_add4(h + 0 * HIST_REP * 256, x ^ rotw, nv);
-            hist_add4(h + 1 * HIST_REP * 256, __vsub4(x, l) ^ rotw, nv);
-            hist_add4(h + 2 * HIST_REP * 256, __vsub4(x, u) ^ rotw, nv);
-            hist_add4(h + 3 * HIST_REP * 256, __vsub4(x, __vhaddu4(l, u)) ^ rotw, nv);
-            hist_add4(h + 4 * HIST_REP * 256, __vsub4(x, paeth4(l, u, ul)) ^ rotw, nv);
-        }
-    }
+    static_assert(HIST_REP == 4, "replica select and rotation are written for four replicas");
+    const uint32_t nfull = len >> 4, rep = threadIdx.x & (HIST_REP - 1), hist_base = smem_u32(hist);
+    for (uint32_t c = threadIdx.x; c < nfull; c += NT) entropy_chunk<D, false>(cur, up, c, 16, shift, hist_base, rep);
+    if ((len & 15u) && threadIdx.x == (nfull % NT)) entropy_chunk<D, true>(cur, up, nfull, (int)(len & 15u), shift, hist_base, rep);
 }
 // sum over present values of ilog2i(count) (strategies.rs:136-142); clears the histograms for the next row.
 template <int NT>
@@ -505,14 +526,6 @@ __device__ __forceinline__ uint32_t ilog2i_z(uint32_t i) {
     uint32_t sh;
     asm("shl.b32 %0, %1, %2;" : "=r"(sh) : "r"(2u), "r"(lg));
     return i * (lg + 2u) - sh;
-}
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { // full prmt (sign-replicate nibbles kept)
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-    return d;
-}
-__device__ __forceinline__ void smem_inc(uint32_t addr) { // no-return add of 1 on a shared-window byte address
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
 }
 // Dense tables, trials 1..4: u32 counters, two lane-selected replicas per trial, 32 KB in all.  Byte offset of the
 // counter of window (first, second) -- both as range codes 0..31 -- of trial f in replica rep:
