@@ -148,8 +148,41 @@ __device__ __forceinline__ uint32_t tail_mask(int valid_bytes) { // bytes of a w
     return valid_bytes >= 4 ? 0xFFFFFFFFu : (valid_bytes <= 0 ? 0u : ((1u << (8 * valid_bytes)) - 1u));
 }
 
-// 16 bytes starting at an arbitrary byte offset of a staged row (shared memory), via 32-bit loads + funnel shifts.
+// 16 bytes starting at an arbitrary byte offset of a staged row (shared memory): the two aligned 16-byte granules that
+// contain them (conflict-free 128-bit loads; a slot has >= 32 bytes of padding on both sides) and funnel shifts.  The
+// misalignment is the same for every thread of a write pass, so the word select is a uniform branch.
+__device__ __forceinline__ uint4 ld_unaligned16_wide(const uint8_t *p) {
+    const uint32_t a = smem_u32(p);
+    const uint32_t s = (a & 3u) * 8u;
+    const uint4 *q = reinterpret_cast<const uint4 *>(p - (a & 15u));
+    const uint4 A = q[0], B = q[1];
+    uint4 r;
+    switch ((a >> 2) & 3u) {
+    case 0:
+        r.x = __funnelshift_r(A.x, A.y, s); r.y = __funnelshift_r(A.y, A.z, s);
+        r.z = __funnelshift_r(A.z, A.w, s); r.w = __funnelshift_r(A.w, B.x, s);
+        break;
+    case 1:
+        r.x = __funnelshift_r(A.y, A.z, s); r.y = __funnelshift_r(A.z, A.w, s);
+        r.z = __funnelshift_r(A.w, B.x, s); r.w = __funnelshift_r(B.x, B.y, s);
+        break;
+    case 2:
+        r.x = __funnelshift_r(A.z, A.w, s); r.y = __funnelshift_r(A.w, B.x, s);
+        r.z = __funnelshift_r(B.x, B.y, s); r.w = __funnelshift_r(B.y, B.z, s);
+        break;
+    default:
+        r.x = __funnelshift_r(A.w, B.x, s); r.y = __funnelshift_r(B.x, B.y, s);
+        r.z = __funnelshift_r(B.y, B.z, s); r.w = __funnelshift_r(B.z, B.w, s);
+        break;
+    }
+    return r;
+}
+
+// The same via five 32-bit loads (4-way bank conflicts, but no branch): cheaper where shared-memory bandwidth is not
+// the limiter.  WIDE is chosen per kernel (the Entropy scorer is bound by shared-memory wavefronts).
+template <bool WIDE>
 __device__ __forceinline__ uint4 ld_unaligned16(const uint8_t *p) {
+    if (WIDE) return ld_unaligned16_wide(p);
     const uint32_t a = smem_u32(p);
     const uint32_t s = (a & 3u) * 8u;
     const uint32_t *q = reinterpret_cast<const uint32_t *>(p - (a & 3u));
@@ -815,7 +848,7 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
 // output are produced in the output's alignment frame; the (at most 31) edge bytes are written one by one.
 // `rot` rotates the thread->granule assignment so that the write passes of several strategies of one row land on
 // different warps (a 4 KB row has 256 granules: 8 of the 32 warps of a 1024-thread CTA).
-template <int NT>
+template <int NT, bool WIDE>
 __device__ __forceinline__ void write_row(int f, const uint8_t *cur, const uint8_t *up, uint32_t len, int bpp,
                                           uint8_t *out_row, int rot = 0) {
     const int tid_r = ((int)threadIdx.x - rot) & (NT - 1);
@@ -825,22 +858,22 @@ __device__ __forceinline__ void write_row(int f, const uint8_t *cur, const uint8
     uint8_t *base = out_row - phase;
     for (int q = 1 + tid_r; q < q_full_end; q += NT) {
         const int i0 = 16 * q - phase - 1; // row byte of the granule's first position (>= 0)
-        const uint4 x = ld_unaligned16(cur + i0);
+        const uint4 x = ld_unaligned16<WIDE>(cur + i0);
         uint4 r;
         if (f == 0) {
             r = x;
         } else if (f == 1) {
-            const uint4 l = ld_unaligned16(cur + i0 - bpp);
+            const uint4 l = ld_unaligned16<WIDE>(cur + i0 - bpp);
             r.x = __vsub4(x.x, l.x); r.y = __vsub4(x.y, l.y); r.z = __vsub4(x.z, l.z); r.w = __vsub4(x.w, l.w);
         } else if (f == 2) {
-            const uint4 u = ld_unaligned16(up + i0);
+            const uint4 u = ld_unaligned16<WIDE>(up + i0);
             r.x = __vsub4(x.x, u.x); r.y = __vsub4(x.y, u.y); r.z = __vsub4(x.z, u.z); r.w = __vsub4(x.w, u.w);
         } else if (f == 3) {
-            const uint4 l = ld_unaligned16(cur + i0 - bpp), u = ld_unaligned16(up + i0);
+            const uint4 l = ld_unaligned16<WIDE>(cur + i0 - bpp), u = ld_unaligned16<WIDE>(up + i0);
             r.x = __vsub4(x.x, __vhaddu4(l.x, u.x)); r.y = __vsub4(x.y, __vhaddu4(l.y, u.y));
             r.z = __vsub4(x.z, __vhaddu4(l.z, u.z)); r.w = __vsub4(x.w, __vhaddu4(l.w, u.w));
         } else {
-            const uint4 l = ld_unaligned16(cur + i0 - bpp), u = ld_unaligned16(up + i0), ul = ld_unaligned16(up + i0 - bpp);
+            const uint4 l = ld_unaligned16<WIDE>(cur + i0 - bpp), u = ld_unaligned16<WIDE>(up + i0), ul = ld_unaligned16<WIDE>(up + i0 - bpp);
             r.x = __vsub4(x.x, paeth4(l.x, u.x, ul.x)); r.y = __vsub4(x.y, paeth4(l.y, u.y, ul.y));
             r.z = __vsub4(x.z, paeth4(l.z, u.z, ul.z)); r.w = __vsub4(x.w, paeth4(l.w, u.w, ul.w));
         }
@@ -1109,7 +1142,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (
                 const int rot = (int)((j2 * g32) & (NT - 1));
                 if ((int)(((int)threadIdx.x - rot) & (NT - 1)) >= (int)g32 + 32) continue;
                 const int f = decided ? (int)fsel[j2] : decide_row(st, r, len, sr, heur, false);
-                write_row<NT>(f, cur, up, len, bpp, st.out + row_off, rot);
+                write_row<NT, (SC & SC_ENTROPY) != 0>(f, cur, up, len, bpp, st.out + row_off, rot);
                 if (tid == rot) st.filters_used[used_off + k] = (uint8_t)f;
             }
             if (row_end_barrier) __syncthreads(); // slot `sp` may be refilled by the next iteration's prefetch
