@@ -284,9 +284,9 @@ def run_ours(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_fast<D=1,SC_BIGRAM> (fused None+Bigrams+BigEnt)",
+                "traffic": traffic, "kernel": "k_fast<D=1,SC_BIGRAM|SC_HALF> (fused None+Bigrams+BigEnt; 256-thread CTAs, 4 per SM)",
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_launch_ms, "peak_source": peak_src,
-                "limiter": "shared-memory atomics (bigram counter table), not HBM"}
+                "limiter": "instruction issue + shared-memory atomics (5 bigram-table updates per input byte), not HBM"}
 
     # --- end to end through the host-buffer C-ABI call (pinned host memory; H2D + D2H inside the timed region)
     e2e = None
