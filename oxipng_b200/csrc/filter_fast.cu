@@ -48,7 +48,7 @@ struct FastParams {
     uint32_t shift; // 8 * (bpp % 4): funnel-shift amount that turns a row word into its "left" word
     uint32_t nslot;     // ring slots (4 when shared memory allows: removes the end-of-row barrier; else 3)
     uint32_t h0_slots;  // bigram scorer with small_tab: slots of the trial-0 hash table (power of two, > 2 * row bytes)
-    uint32_t small_tab; // bigram scorer: five dense 64x64 in-range tables are carved (rows <= 8192 bytes)
+    uint32_t small_tab; // bigram scorer: the dense-table layout is carved (rows <= 16384 bytes)
 };
 
 __host__ __device__ constexpr int threads_for(int sc) { return (sc & SC_HALF) ? HALF_NT : (sc & SC_BIGRAM) ? 1024 : sc == SC_ENTROPY ? 512 : 256; }
@@ -456,7 +456,7 @@ __device__ __forceinline__ void bigram_row(const uint8_t *cur, const uint8_t *up
     bigram_trial<D, NT, 4, WPT>(cur, up, len, shift, bpp, table, s_bgc, s_bge);
 }
 
-// ---- Bigrams/BigEnt, all five trials at once (rows <= 8192 bytes) ---------------------------------------------------
+// ---- Bigrams/BigEnt, all five trials at once (rows <= 16384 bytes) --------------------------------------------------
 // Filtered rows of natural images are sharply peaked around 0, which makes atomics on one shared table serialise
 // (ncu: 10-32 wavefronts per ATOMS; same-address lanes serialise with or without a return value), and a directly
 // indexed table of all 65536 bigrams (128 KB) limits the SM to one CTA.  Instead, per row:
@@ -471,10 +471,10 @@ __device__ __forceinline__ void bigram_row(const uint8_t *cur, const uint8_t *up
 //    re-derived from the staged row and counted in h0, trial by trial, after h0 has been swept.
 // Exact for any data: every window is counted in exactly one structure, and their key sets are disjoint.
 
-// h0 entries are ((key + 1) << 14) | count: key + 1 is never 0, and a count is at most 8192 (row bytes).
+// h0 entries are ((key + 1) << 15) | count: key + 1 is never 0 (and at most 2^16), a count is at most 16384 (row bytes).
 __device__ __forceinline__ void h0_collide(uint32_t *h, uint32_t s, uint32_t tag, uint32_t old, uint32_t mask) {
     for (;;) {
-        if ((old & ~0x3FFFu) == tag) {
+        if ((old & ~0x7FFFu) == tag) {
             atomicAdd(&h[s], 1u);
             return;
         }
@@ -485,7 +485,7 @@ __device__ __forceinline__ void h0_collide(uint32_t *h, uint32_t s, uint32_t tag
 }
 __device__ __forceinline__ uint32_t h0_slot(uint32_t key, uint32_t hshift) { return (key * 0x9E3779B1u) >> hshift; }
 __device__ __forceinline__ void h0_add(uint32_t *h, uint32_t key, uint32_t hshift, uint32_t mask) {
-    const uint32_t tag = (key + 1u) << 14, s = h0_slot(key, hshift);
+    const uint32_t tag = (key + 1u) << 15, s = h0_slot(key, hshift);
     const uint32_t old = atomicCAS(&h[s], 0u, tag | 1u);
     if (old != 0) h0_collide(h, s, tag, old, mask);
 }
@@ -497,7 +497,7 @@ __device__ __forceinline__ void h0_sweep(uint32_t *h, uint32_t slots, uint32_t &
         const uint4 v = h4[q];
         if (v.x | v.y | v.z | v.w) {
             h4[q] = make_uint4(0, 0, 0, 0);
-            const uint32_t c0 = v.x & 0x3FFFu, c1 = v.y & 0x3FFFu, c2 = v.z & 0x3FFFu, c3 = v.w & 0x3FFFu;
+            const uint32_t c0 = v.x & 0x7FFFu, c1 = v.y & 0x7FFFu, c2 = v.z & 0x7FFFu, c3 = v.w & 0x7FFFu;
             d += (c0 != 0) + (c1 != 0) + (c2 != 0) + (c3 != 0);
             if (c0 > 1) e += ilog2i(c0);
             if (c1 > 1) e += ilog2i(c1);
@@ -508,7 +508,7 @@ __device__ __forceinline__ void h0_sweep(uint32_t *h, uint32_t slots, uint32_t &
 }
 
 // Outlier keys of trials 1..4 are never 0 (one of the two bytes lies outside [-16, 15]), so an empty slot is 0; a count
-// is at most the number of windows of a row (<= 8192), so it cannot reach the key bits.  Returns false when no slot was
+// is at most the number of windows of a row (<= 16384), so it cannot reach the key bits.  Returns false when no slot was
 // found within HPROBE probes (table crowded): the caller then flags the trial.
 __device__ __forceinline__ bool ohash_add(uint32_t *h, uint32_t key) {
     uint32_t s = ((key * 40503u) >> 7) & (HSLOTS - 1);
@@ -653,7 +653,7 @@ __device__ __noinline__ void bigram_exact0(const uint8_t *cur, uint32_t len, uin
     __syncthreads();
 }
 
-// Per row (rows <= 8192 bytes):
+// Per row (rows <= 16384 bytes):
 //  * trials 1..4: a window whose two stream bytes both lie in [-16, 15] (as i8) is counted in a dense 32x32 table of
 //    its trial (two lane-selected replicas, bank = first ^ second); the remaining (outlier) windows go to a small
 //    open-addressing hash table of (key, count) per trial;
@@ -824,10 +824,28 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
     __syncthreads(); // h0 is clean
     for (int f = 1; f < 5; f++) {
         if (!((flagged >> (f - 1)) & 1u)) continue;
-        for (uint32_t p = threadIdx.x; p < len; p += NT) {
-            const uint32_t b = residual_at(f, cur, up, (int)p, bpp);
-            const uint32_t pr = p ? residual_at(f, cur, up, (int)p - 1, bpp) : (uint32_t)f;
-            if ((((pr + 16u) | (b + 16u)) & 0xE0u) != 0) h0_add(h0, (pr << 8) | b, hshift, hmask);
+        // word-granular: thread t rebuilds the residual words t, t+NT, ... byte-SIMD; the byte in front of a word comes
+        // from the neighbouring lane (lane 0: one scalar pixel, or the filter id in front of word 0)
+        const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur), *uw = reinterpret_cast<const uint32_t *>(up);
+        for (uint32_t k = threadIdx.x; k < ((nwords + 31u) & ~31u); k += NT) {
+            const int kk = (int)k;
+            uint32_t r = 0;
+            if (k < nwords) {
+                const uint32_t x = cw[kk], u = uw[kk];
+                const uint32_t l = D == 2 ? cw[kk - 2] : D == 1 ? __funnelshift_l(cw[kk - 2], cw[kk - 1], shift)
+                                                                 : __funnelshift_l(cw[kk - 1], cw[kk], shift);
+                const uint32_t ul = D == 2 ? uw[kk - 2] : D == 1 ? __funnelshift_l(uw[kk - 2], uw[kk - 1], shift)
+                                                                  : __funnelshift_l(uw[kk - 1], uw[kk], shift);
+                r = __vsub4(x, pred4_rt(f, l, u, ul));
+            }
+            uint32_t pr = __shfl_up_sync(0xffffffffu, r >> 24, 1);
+            if (lane == 0) pr = k == 0 ? (uint32_t)f : (k < nwords ? residual_at(f, cur, up, 4 * kk - 1, bpp) : 0u);
+            const int valid = (int)len - 4 * kk;
+            for (int j = 0; j < 4 && j < valid; j++) {
+                const uint32_t b = (r >> (8 * j)) & 255u;
+                if ((((pr + 16u) | (b + 16u)) & 0xE0u) != 0) h0_add(h0, (pr << 8) | b, hshift, hmask);
+                pr = b;
+            }
         }
         __syncthreads();
         uint32_t d = 0, e = 0;
@@ -1213,10 +1231,10 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
     P.n_images = n_images;
     P.rb = slot_bytes(g);
     P.shift = 8 * (g.bpp % 4);
-    // bigram scorer, rows <= 8192 bytes: hash of whole rows (> 2 slots per window) + dense tables + outlier hashes
+    // bigram scorer, rows <= 16384 bytes: dense tables + outlier hashes + hash of whole rows (>= 2 slots per window)
     uint32_t h0 = 1024;
     while (h0 < 2 * g.max_len) h0 *= 2;
-    P.small_tab = (sc & SC_BIGRAM) && g.max_len <= 8192 && smem_bytes_for(sc, P.rb, h0) <= SMEM_LIMIT;
+    P.small_tab = (sc & SC_BIGRAM) && g.max_len <= 16384 && smem_bytes_for(sc, P.rb, h0) <= SMEM_LIMIT;
     P.h0_slots = P.small_tab ? h0 : 0;
     // ... and with rows <= 4096 bytes two 512-thread CTAs fit an SM (two rows in flight: one CTA's barriers and table
     // sweeps overlap the other's counting)

@@ -30,6 +30,9 @@ cfg = {
     "c3a": (4096, 4096, 4, 16, [S.Bigrams, S.BigEnt], 1),
     "c3b": (4096, 4096, 4, 8, [S.Bigrams, S.BigEnt], 1),
     "c5": (1024, 1024, 4, 8, [S.NONE, S.Bigrams, S.BigEnt], a.images),
+    "c1bg": (4096, 4096, 4, 8, [S.Bigrams, S.BigEnt], 1),       # 16 KB rows, photo content
+    "c1bg2k": (2048, 8192, 4, 8, [S.Bigrams, S.BigEnt], 1),     # 8 KB rows, photo content
+    "c5rand": (1024, 1024, 4, 8, [S.NONE, S.Bigrams, S.BigEnt], a.images),  # noise: every window is an outlier
 }[a.config]
 w, h, ch, bd, strat, n = cfg
 if n == 1:
@@ -40,10 +43,13 @@ interlaced = a.config == "c3b"
 hdr = ox.IhdrData(w, h, ct, ox.BitDepth(bd), interlaced)
 per = w * h * ch * (bd // 8)
 d = synth.photo_batch(n, w, h, ch, bd, 0xB2000001, dev)
+if a.config == "c5rand":
+    d = torch.randint(0, 256, d.shape, dtype=torch.uint8, device=dev)
 if interlaced:
-    # Adam7 layout of the same bytes: the generator's rows are reinterpreted pass by pass (content differs from the
-    # progressive image but has the same statistics); geometry is what the kernel sees.
-    pass
+    # the same image in the Adam7 layout (oxi_interlace_image, interlace.rs:6-60): every pass is a subsampled picture
+    prog = ox.PngImage(ox.IhdrData(w, h, ct, ox.BitDepth(bd), False), d.cpu().numpy())
+    d = torch.from_numpy(ox.interlace_image(prog).data.copy()).to(dev)
+    per = d.numel()
 rows = ox.lib().oxi_num_scanlines(__import__("ctypes").byref(hdr._c()), per)
 o = [torch.empty(n * (per + rows), dtype=torch.uint8, device=dev) for _ in strat]
 u = [torch.empty(n * rows, dtype=torch.uint8, device=dev) for _ in strat]

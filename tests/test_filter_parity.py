@@ -186,7 +186,8 @@ def test_bigram_none_trial_bounds_and_exact_pass():
     Sub/Up are as good as None."""
     import oxipng_b200 as ox
     rng = np.random.default_rng(4242)
-    for (w, h, ct) in [(1024, 24, 6), (333, 17, 2), (2048, 9, 0)]:
+    # (4096 px RGBA8 = 16 KB rows: the longest rows of the dense-table path; a constant row there has one bigram 16384 times)
+    for (w, h, ct) in [(1024, 24, 6), (333, 17, 2), (2048, 9, 0), (4096, 8, 6), (3000, 8, 6)]:
         ch = {0: 1, 2: 3, 6: 4}[ct]
         L = w * ch
         rows = []
