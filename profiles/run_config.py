@@ -33,6 +33,9 @@ cfg = {
     "c1bg": (4096, 4096, 4, 8, [S.Bigrams, S.BigEnt], 1),       # 16 KB rows, photo content
     "c1bg2k": (2048, 8192, 4, 8, [S.Bigrams, S.BigEnt], 1),     # 8 KB rows, photo content
     "c5rand": (1024, 1024, 4, 8, [S.NONE, S.Bigrams, S.BigEnt], a.images),  # noise: every window is an outlier
+    "c5n6": (1024, 1024, 4, 8, [S.NONE, S.Bigrams, S.BigEnt], a.images),
+    "c5n12": (1024, 1024, 4, 8, [S.NONE, S.Bigrams, S.BigEnt], a.images),
+    "c5n24": (1024, 1024, 4, 8, [S.NONE, S.Bigrams, S.BigEnt], a.images),
 }[a.config]
 w, h, ch, bd, strat, n = cfg
 if n == 1:
@@ -45,6 +48,11 @@ per = w * h * ch * (bd // 8)
 d = synth.photo_batch(n, w, h, ch, bd, 0xB2000001, dev)
 if a.config == "c5rand":
     d = torch.randint(0, 256, d.shape, dtype=torch.uint8, device=dev)
+if a.config.startswith("c5n"):  # photo + extra uniform noise in [-A, A] on the colour channels (A = 6, 12, 24 ...)
+    A = int(a.config[3:])
+    nz = torch.randint(-A, A + 1, d.shape, dtype=torch.int16, device=dev)
+    nz[3::4] = 0
+    d = ((d.to(torch.int16) + nz) & 255).to(torch.uint8)
 if interlaced:
     # the same image in the Adam7 layout (oxi_interlace_image, interlace.rs:6-60): every pass is a subsampled picture
     prog = ox.PngImage(ox.IhdrData(w, h, ct, ox.BitDepth(bd), False), d.cpu().numpy())
