@@ -260,20 +260,22 @@ __host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, uint32_t h0_slots, 
 
 // MinSum for all five filters in one sweep. Accumulates S_f = sum over bytes of ||cur-pred_f| - 128|; the caller turns
 // it into the reference's score 128*bytes - S_f + f (the filter-type byte f counts |f| = f, png/mod.rs:409-414).
-// Returns the OR of this thread's row words (for the all-zero-row test, so that no separate scan is needed).
-template <int D, bool TAIL>
+// S_0 also answers the all-zero-row test: ||x| - 128| is 128 only for x = 0, so S_0 = 128 * bytes iff the row is zero.
+// S0: bpp = 4 (the funnel shift that forms "left" is by zero bits: a plain register pick).
+template <int D, bool TAIL, bool S0>
 __device__ __forceinline__ void minsum_chunk(const uint8_t *cur, const uint8_t *up, uint32_t c, int valid, uint32_t shift,
-                                             uint32_t (&a)[5], uint32_t &nz) {
+                                             uint32_t (&a)[5]) {
     const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
     const uint32_t H = 0x80808080u;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        uint32_t x = cw.w[k + 2], u = uw.w[k + 2], l = left_word<D>(cw, k, shift), ul = left_word<D>(uw, k, shift);
+        uint32_t x = cw.w[k + 2], u = uw.w[k + 2];
+        uint32_t l = (S0 && D == 1) ? cw.w[k + 1] : left_word<D>(cw, k, shift);
+        uint32_t ul = (S0 && D == 1) ? uw.w[k + 1] : left_word<D>(uw, k, shift);
         if (TAIL) { // last, partial chunk: bytes past the row contribute |0-0| -> cancel exactly
             const uint32_t m = tail_mask(valid - 4 * k);
             x &= m; u &= m; l &= m; ul &= m;
         }
-        nz |= x;
         a[0] = __vsadu4(x, H) + a[0];
         a[1] = __vsadu4(__vabsdiffu4(x, l), H) + a[1];
         a[2] = __vsadu4(__vabsdiffu4(x, u), H) + a[2];
@@ -282,18 +284,21 @@ __device__ __forceinline__ void minsum_chunk(const uint8_t *cur, const uint8_t *
     }
 }
 template <int D, int NT>
-__device__ __forceinline__ uint32_t minsum_pass(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
-                                                uint32_t *s_min) {
+__device__ __forceinline__ void minsum_pass(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
+                                            uint32_t *s_min) {
     const uint32_t nfull = len >> 4; // complete 16-byte chunks: no masking in the main loop
-    uint32_t a[5] = {0, 0, 0, 0, 0}, nz = 0;
-    for (uint32_t c = threadIdx.x; c < nfull; c += NT) minsum_chunk<D, false>(cur, up, c, 16, shift, a, nz);
-    if ((len & 15u) && threadIdx.x == (nfull % NT)) minsum_chunk<D, true>(cur, up, nfull, (int)(len & 15u), shift, a, nz);
+    uint32_t a[5] = {0, 0, 0, 0, 0};
+    if (D == 1 && shift == 0) {
+        for (uint32_t c = threadIdx.x; c < nfull; c += NT) minsum_chunk<D, false, true>(cur, up, c, 16, shift, a);
+    } else {
+        for (uint32_t c = threadIdx.x; c < nfull; c += NT) minsum_chunk<D, false, false>(cur, up, c, 16, shift, a);
+    }
+    if ((len & 15u) && threadIdx.x == (nfull % NT)) minsum_chunk<D, true, false>(cur, up, nfull, (int)(len & 15u), shift, a);
     a[0] = warp_sum(a[0]); a[1] = warp_sum(a[1]); a[2] = warp_sum(a[2]); a[3] = warp_sum(a[3]); a[4] = warp_sum(a[4]);
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&s_min[0], a[0]); atomicAdd(&s_min[1], a[1]); atomicAdd(&s_min[2], a[2]);
         atomicAdd(&s_min[3], a[3]); atomicAdd(&s_min[4], a[4]);
     }
-    return nz;
 }
 
 // Entropy: histogram the residual bytes of all five filters (filter-type byte added at scoring time).  The counter of
@@ -1080,7 +1085,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (
                 if (tid < (int)SCORE_WORDS) sm.sc[set_next * SCORE_WORDS + tid] = 0;
                 uint32_t nz = 0;
                 bool small_flow = false;
-                if (SC & SC_MINSUM) nz = minsum_pass<D, NT>(cur, up, len, shift, sr.s_min_());
+                if (SC & SC_MINSUM) minsum_pass<D, NT>(cur, up, len, shift, sr.s_min_());
                 if (SC & SC_ENTROPY) {
                     entropy_pass<D, NT>(cur, up, len, shift, sm.hist);
                     __syncthreads();
@@ -1136,19 +1141,23 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (
                     decided = true;
                 } else {
                     // all-zero rows short-circuit to None (png/mod.rs:398-404); decided at the scorers' last barrier
-                    // (the MinSum sweep has already OR-ed the row)
-                    const uint4 *c4 = reinterpret_cast<const uint4 *>(cur);
-                    const uint32_t nchunks = (SC & SC_MINSUM) ? 0u : (len + 15) >> 4;
-                    for (uint32_t c = tid; c < nchunks; c += NT) {
-                        uint4 v = c4[c];
-                        const int valid = (int)len - (int)(16 * c);
-                        if (valid < 16) {
-                            v.x &= tail_mask(valid); v.y &= tail_mask(valid - 4); v.z &= tail_mask(valid - 8);
-                            v.w &= tail_mask(valid - 12);
+                    if (SC & SC_MINSUM) { // S_0 = 128 per byte iff every byte is zero (see minsum_chunk)
+                        __syncthreads();
+                        heur = sr.s_min_()[0] != 128u * 16u * ((len + 15u) >> 4);
+                    } else {
+                        const uint4 *c4 = reinterpret_cast<const uint4 *>(cur);
+                        const uint32_t nchunks = (len + 15) >> 4;
+                        for (uint32_t c = tid; c < nchunks; c += NT) {
+                            uint4 v = c4[c];
+                            const int valid = (int)len - (int)(16 * c);
+                            if (valid < 16) {
+                                v.x &= tail_mask(valid); v.y &= tail_mask(valid - 4); v.z &= tail_mask(valid - 8);
+                                v.w &= tail_mask(valid - 12);
+                            }
+                            nz |= v.x | v.y | v.z | v.w;
                         }
-                        nz |= v.x | v.y | v.z | v.w;
+                        heur = __syncthreads_or(nz != 0) != 0;
                     }
-                    heur = __syncthreads_or(nz != 0) != 0;
                 }
                 set_cur = set_next;
             }
