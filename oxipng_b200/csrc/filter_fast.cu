@@ -588,9 +588,9 @@ __device__ __forceinline__ void dense_word(uint32_t tr, uint32_t tpr, uint32_t d
     smem_inc(dense_base + prmt(lo, hi, 0xFF73u));
 }
 // the same word window by window: tail words and words with an out-of-range byte (t, tprev unrotated)
-template <int F>
-__device__ __noinline__ void dense_word_slow(uint32_t t, uint32_t tprev, int valid, uint32_t dense_base, uint32_t rep,
-                                             uint32_t *ohash, uint32_t *s_out) {
+// (one copy for all trials, F at run time: this path is off the straight line and should stay small in the i-cache)
+__device__ __noinline__ void dense_word_slow(uint32_t F, uint32_t t, uint32_t tprev, int valid, uint32_t dense_base,
+                                             uint32_t rep, uint32_t *ohash, uint32_t *s_out) {
     uint32_t tp = tprev >> 24;
     for (int j = 0; j < 4; j++) {
         const uint32_t tj = (t >> (8 * j)) & 255u;
@@ -756,10 +756,7 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
                         if (f == 2) dense_word<3>(tr, tpr, dense_base, c1, c2);
                         if (f == 3) dense_word<4>(tr, tpr, dense_base, c1, c2);
                     } else {
-                        if (f == 0) dense_word_slow<1>(t[f][i], tp, valid, dense_base, rep, sm.ohash, sm.s_out_());
-                        if (f == 1) dense_word_slow<2>(t[f][i], tp, valid, dense_base, rep, sm.ohash, sm.s_out_());
-                        if (f == 2) dense_word_slow<3>(t[f][i], tp, valid, dense_base, rep, sm.ohash, sm.s_out_());
-                        if (f == 3) dense_word_slow<4>(t[f][i], tp, valid, dense_base, rep, sm.ohash, sm.s_out_());
+                        dense_word_slow((uint32_t)f + 1u, t[f][i], tp, valid, dense_base, rep, sm.ohash, sm.s_out_());
                     }
                 }
             }
