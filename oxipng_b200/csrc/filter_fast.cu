@@ -673,6 +673,53 @@ __device__ __noinline__ void bigram_exact0(const uint8_t *cur, uint32_t len, uin
 //  * a trial whose outliers crowd its small hash in some row (noise-like data) is flagged; its outliers are then
 //    re-derived from the staged row and counted in h0, trial by trial.
 // Exact for any data: every window is counted in exactly one structure, and their key sets are disjoint.
+// Flagged trials (their outlier hash crowded in this row): the outlier windows, re-derived from the staged row, are
+// counted in h0, one trial at a time.  Off the straight line: kept out of line for the instruction cache.
+template <int D, int NT>
+__device__ __noinline__ void bigram_flagged(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
+                                            const Smem &sm, uint32_t h0_slots, uint32_t flagged) {
+    const uint32_t nwords = (len + 3) >> 2, lane = threadIdx.x & 31u;
+    uint32_t *h0 = sm.table;
+    const uint32_t hmask = h0_slots - 1, hshift = (uint32_t)__clz((int)h0_slots) + 1;
+    __syncthreads(); // h0 is clean
+    for (int f = 1; f < 5; f++) {
+        if (!((flagged >> (f - 1)) & 1u)) continue;
+        // word-granular: thread t rebuilds the residual words t, t+NT, ... byte-SIMD; the byte in front of a word comes
+        // from the neighbouring lane (lane 0: one scalar pixel, or the filter id in front of word 0)
+        const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur), *uw = reinterpret_cast<const uint32_t *>(up);
+        for (uint32_t k = threadIdx.x; k < ((nwords + 31u) & ~31u); k += NT) {
+            const int kk = (int)k;
+            uint32_t r = 0;
+            if (k < nwords) {
+                const uint32_t x = cw[kk], u = uw[kk];
+                const uint32_t l = D == 2 ? cw[kk - 2] : D == 1 ? __funnelshift_l(cw[kk - 2], cw[kk - 1], shift)
+                                                                 : __funnelshift_l(cw[kk - 1], cw[kk], shift);
+                const uint32_t ul = D == 2 ? uw[kk - 2] : D == 1 ? __funnelshift_l(uw[kk - 2], uw[kk - 1], shift)
+                                                                  : __funnelshift_l(uw[kk - 1], uw[kk], shift);
+                r = __vsub4(x, pred4_rt(f, l, u, ul));
+            }
+            uint32_t pr = __shfl_up_sync(0xffffffffu, r >> 24, 1);
+            if (lane == 0) pr = k == 0 ? (uint32_t)f : (k < nwords ? residual_at(f, cur, up, 4 * kk - 1, bpp) : 0u);
+            const int valid = (int)len - 4 * kk;
+            for (int j = 0; j < 4 && j < valid; j++) {
+                const uint32_t b = (r >> (8 * j)) & 255u;
+                if ((((pr + 16u) | (b + 16u)) & 0xE0u) != 0) h0_add(h0, (pr << 8) | b, hshift, hmask);
+                pr = b;
+            }
+        }
+        __syncthreads();
+        uint32_t d = 0, e = 0;
+        h0_sweep<NT>(h0, h0_slots, d, e);
+        d = warp_sum(d);
+        e = warp_sum(e);
+        if ((threadIdx.x & 31) == 0 && d) {
+            atomicAdd(&sm.s_bgc_()[f], d);
+            atomicAdd(&sm.s_bge_()[f], e);
+        }
+        __syncthreads();
+    }
+}
+
 template <int D, int NT>
 __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
                                                      const Smem &sm, uint32_t h0_slots, const Prefetch &pf) {
@@ -823,43 +870,7 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
     // flagged trials: their outlier windows, re-derived from the staged row, are counted in h0, one trial at a time
     const uint32_t flagged = sm.s_out_()[1] | sm.s_out_()[2] << 1 | sm.s_out_()[3] << 2 | sm.s_out_()[4] << 3; // uniform
     if (flagged == 0) return nz;
-    __syncthreads(); // h0 is clean
-    for (int f = 1; f < 5; f++) {
-        if (!((flagged >> (f - 1)) & 1u)) continue;
-        // word-granular: thread t rebuilds the residual words t, t+NT, ... byte-SIMD; the byte in front of a word comes
-        // from the neighbouring lane (lane 0: one scalar pixel, or the filter id in front of word 0)
-        const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur), *uw = reinterpret_cast<const uint32_t *>(up);
-        for (uint32_t k = threadIdx.x; k < ((nwords + 31u) & ~31u); k += NT) {
-            const int kk = (int)k;
-            uint32_t r = 0;
-            if (k < nwords) {
-                const uint32_t x = cw[kk], u = uw[kk];
-                const uint32_t l = D == 2 ? cw[kk - 2] : D == 1 ? __funnelshift_l(cw[kk - 2], cw[kk - 1], shift)
-                                                                 : __funnelshift_l(cw[kk - 1], cw[kk], shift);
-                const uint32_t ul = D == 2 ? uw[kk - 2] : D == 1 ? __funnelshift_l(uw[kk - 2], uw[kk - 1], shift)
-                                                                  : __funnelshift_l(uw[kk - 1], uw[kk], shift);
-                r = __vsub4(x, pred4_rt(f, l, u, ul));
-            }
-            uint32_t pr = __shfl_up_sync(0xffffffffu, r >> 24, 1);
-            if (lane == 0) pr = k == 0 ? (uint32_t)f : (k < nwords ? residual_at(f, cur, up, 4 * kk - 1, bpp) : 0u);
-            const int valid = (int)len - 4 * kk;
-            for (int j = 0; j < 4 && j < valid; j++) {
-                const uint32_t b = (r >> (8 * j)) & 255u;
-                if ((((pr + 16u) | (b + 16u)) & 0xE0u) != 0) h0_add(h0, (pr << 8) | b, hshift, hmask);
-                pr = b;
-            }
-        }
-        __syncthreads();
-        uint32_t d = 0, e = 0;
-        h0_sweep<NT>(h0, h0_slots, d, e);
-        d = warp_sum(d);
-        e = warp_sum(e);
-        if ((threadIdx.x & 31) == 0 && d) {
-            atomicAdd(&sm.s_bgc_()[f], d);
-            atomicAdd(&sm.s_bge_()[f], e);
-        }
-        __syncthreads();
-    }
+    bigram_flagged<D, NT>(cur, up, len, shift, bpp, sm, h0_slots, flagged);
     return nz;
 }
 
@@ -926,7 +937,7 @@ __device__ __forceinline__ void coop_load_row(uint8_t *dst, const uint8_t *src, 
 // The filter a strategy uses for one row (png/mod.rs:385-421): fixed for Basic / Predefined; for the heuristics the
 // winner of the five trials under the reference's strict comparisons in RowFilter::ALL order (lowest id wins ties),
 // None for all-zero rows.  `exact0`: the exact Bigrams/BigEnt scores of trial 0 are in slot 5 (bigram_exact0).
-__device__ __forceinline__ int decide_row(const DevStrategy &st, uint32_t r, uint32_t len, const Smem &sr, bool heur, bool exact0) {
+__device__ __noinline__ int decide_row(const DevStrategy &st, uint32_t r, uint32_t len, const Smem &sr, bool heur, bool exact0) {
     int f = 0;
     if (st.kind == OXI_BASIC) {
         f = st.basic;
