@@ -543,7 +543,7 @@ struct Prefetch {
     uint64_t *bar;
 };
 template <int NT>
-__device__ __forceinline__ void coop_load_row(uint8_t *dst, const uint8_t *src, uint32_t len);
+__device__ __noinline__ void coop_load_row(uint8_t *dst, const uint8_t *src, uint32_t len);
 template <int NT>
 __device__ __forceinline__ void issue_prefetch(const Prefetch &pf) {
     if (!pf.on) return;
@@ -922,7 +922,7 @@ __device__ __forceinline__ void write_row(int f, const uint8_t *cur, const uint8
 
 // cooperative, alignment-agnostic row load (rows that TMA cannot take: not 16-byte aligned / sized)
 template <int NT>
-__device__ __forceinline__ void coop_load_row(uint8_t *dst, const uint8_t *src, uint32_t len) {
+__device__ __noinline__ void coop_load_row(uint8_t *dst, const uint8_t *src, uint32_t len) {
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
     const uint32_t *g = reinterpret_cast<const uint32_t *>(src - mis);
     const uint32_t nsrc = (len + mis + 3) >> 2, ndst = (len + 3) >> 2, s = 8 * mis;
