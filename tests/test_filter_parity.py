@@ -220,6 +220,29 @@ def test_bigram_none_trial_bounds_and_exact_pass():
                strategies=["MinSum", "Entropy", "Bigrams", "BigEnt"], label="none-bounds-all")
 
 
+def test_randomised_shapes_fast_tier():
+    """Differential sweep over random widths / heights / pixel formats / contents through the fast tier: odd numbers of
+    row words (the bigram scorer works on word pairs), tails of 1..3 bytes, every filter-bpp (1, 2, 3, 4, 6, 8), rows that
+    cross the 256-thread / 1024-thread kernel boundary (4 KB) and the dense-table limit (16 KB)."""
+    import oxipng_b200 as ox
+    rng = np.random.default_rng(20261020)
+    fmts = [(0, 8), (4, 8), (2, 8), (6, 8), (0, 16), (4, 16), (2, 16), (6, 16), (3, 8)]
+    for it in range(36):
+        ct, bd = fmts[int(rng.integers(len(fmts)))]
+        ch = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ct]
+        maxw = 17000 // (ch * bd // 8)
+        w = int(rng.integers(1, maxw)) if it % 3 else int(rng.integers(1, 64))
+        h = int(rng.integers(1, 9))
+        kind = ["photo", "random", "flat", "photo"][int(rng.integers(4))]
+        ih, d = helpers.synth_image(w, h, ct, bd, 7000 + it, kind)
+        pal = np.zeros((256, 4), np.uint8) if ct == 3 else None
+        _check(ih, d, palette=pal, alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["Bigrams", "BigEnt"],
+               label=f"rnd/{it}/{w}x{h}/{ct}/{bd}/{kind}")
+        if it % 4 == 0:
+            _check(ih, d, palette=pal, alphas=(False,), strategies=["None", "MinSum", "Entropy", "Bigrams", "BigEnt"],
+                   label=f"rnd-all/{it}/{w}x{h}/{ct}/{bd}/{kind}")
+
+
 def test_fast_tier_batch_many_images():
     import oxipng_b200 as ox
     n = 37
