@@ -68,6 +68,30 @@ __device__ __forceinline__ uint32_t paeth(uint32_t a, uint32_t b, uint32_t c) {
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
 }
 
+// ---- byte-SIMD Paeth (shared by the filter search and unfilter_image) ------------------------------------------
+__device__ __forceinline__ uint32_t signmask4(uint32_t x) { // 0xFF in every byte whose MSB is set
+    uint32_t d;                                             // (prmt's sign-replicate selectors; __byte_perm masks them off)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xba98u));
+    return d;
+}
+__device__ __forceinline__ uint32_t sel4(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
+
+// paeth_predictor (src/filters/mod.rs:242-254) on four byte lanes, without widening.
+// a=left, b=up, c=upleft.  pa=|b-c|, pb=|a-c|.  pc=|a+b-2c| equals |pa-pb| when c lies between a and b and pa+pb
+// (>= both) otherwise; "otherwise" is detected as |pa-pb| == |a-b| and pc saturated to 255, which keeps both
+// comparisons against pc true.  Then the winner is the closer of a/b (ties -> a) if its distance <= pc, else c.
+// Checked exhaustively over all 2^24 (a,b,c) on the host.
+__device__ __forceinline__ uint32_t paeth4(uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t pa = __vabsdiffu4(b, c), pb = __vabsdiffu4(a, c);
+    const uint32_t pd = __vabsdiffu4(pa, pb);
+    const uint32_t pc = pd | __vcmpeq4(pd, __vabsdiffu4(a, b));
+    const uint32_t le = __vcmpleu4(pa, pb);
+    const uint32_t w = sel4(le, a, b), mn = sel4(le, pa, pb);
+    // mn <= pc: mn < 128 whenever pc < 255, so (pc|0x80)-mn never borrows and its MSB decides for pc < 128
+    const uint32_t t = (pc | 0x80808080u) - mn;
+    return sel4(signmask4(t | pc), w, c);
+}
+
 // ilog2i, src/filters/strategies.rs:269-272 (i >= 1)
 __device__ __forceinline__ uint32_t ilog2i(uint32_t i) {
     // i * lg + ((i - 2^lg) << 1), written as one multiply-add: i * (lg + 2) - 2^(lg + 1)

@@ -589,19 +589,27 @@ __device__ __forceinline__ void st_bytes(uint8_t *p, uint32_t v, int n) {
         for (int j = 0; j < n; j++) p[j] = (uint8_t)(v >> (8 * j));
     }
 }
-// One CTA per (image, pass); its warps take the 32-row tiles round-robin and run them as a pipeline: the warp of
-// tile t trails the warp of tile t-1 by 32 steps, because row 32t-1 (the row above its first row) is produced by lane
-// 31 of that warp.  Progress is published in shared memory every UF_CHUNK steps; the boundary row itself goes through
-// global memory (stores are fenced before the progress word is updated, the reader bypasses L1 with ld.global.cg).
-constexpr int UF_WARPS = 32, UF_CHUNK = 32;
+// UF_CTAS CTAs per (image, pass); their UF_CTAS x UF_WARPS warps take the 32-row tiles round-robin and run them as a
+// pipeline: the warp of tile t trails the warp of tile t-1 by 32 steps, because row 32t-1 (the row above its first row)
+// is produced by lane 31 of that warp.  Progress is published per warp in global memory every UF_CHUNK steps (the
+// pipeline spans SMs: one SM alone is bound by instruction issue, ~140 instructions per warp and step); the boundary row
+// goes through global memory as well (stores are fenced at device scope before the progress word is updated, the reader
+// bypasses L1 with ld.global.cg).  All CTAs of a launch are resident at once (grid <= 7 x 32 CTAs of 128 threads), so
+// waiting on an earlier tile cannot deadlock.
+// Memory latency stays off the step-to-step dependency chain: at the start of a chunk every lane fetches the filtered
+// bytes of its next UF_CHUNK pixels (and lane 0 the boundary pixels above them) with independent loads into a
+// per-warp shared-memory stage laid out [step][lane] (conflict-free), and the steps then read shared memory only.
+constexpr int UF_WARPS = 4, UF_CTAS = 32, UF_CHUNK = 32;
+constexpr uint32_t UF_STAGE_WORDS = 2 * UF_CHUNK * 32 + 2 * UF_CHUNK; // per warp: W0,W1[step][lane], B0,B1[step]
 __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_t *__restrict__ in, uint8_t *out,
-                                                            uint64_t n_images, uint64_t in_stride, ScanState *st) {
-    __shared__ unsigned long long progress[UF_WARPS]; // (tile << 32) | steps finished, per warp
+                                                            uint64_t n_images, uint64_t in_stride, ScanState *st,
+                                                            unsigned long long *progress) {
+    __shared__ __align__(16) uint32_t uf_stage[UF_WARPS * UF_STAGE_WORDS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) progress[warp] = 0;
-    __syncthreads();
-    const uint64_t item = blockIdx.x;
+    uint32_t *W0 = uf_stage + warp * UF_STAGE_WORDS, *W1 = W0 + UF_CHUNK * 32, *B0 = W1 + UF_CHUNK * 32, *B1 = B0 + UF_CHUNK;
+    const uint64_t item = blockIdx.x / UF_CTAS; // (image, pass)
     if (item >= n_images * g.n_pass) return;
+    const uint32_t gw = (blockIdx.x % UF_CTAS) * UF_WARPS + warp, NW = UF_CTAS * UF_WARPS; // warp of the item's pipeline
     const uint64_t img = item / g.n_pass;
     const PassDesc pd = g.pass[item % g.n_pass];
     const int bpp = (int)g.bpp, n0 = bpp < 4 ? bpp : 4, n1 = bpp - n0; // pixel = word0 (n0 bytes) + word1 (n1 bytes)
@@ -610,48 +618,71 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
     const uint8_t *src = in + img * in_stride + pd.in_base + pd.row0;
     uint8_t *dst = out + img * g.data_len + pd.in_base;
     const uint32_t ntiles = (pd.nrows + 31) / 32, steps = npix + 31;
-    volatile unsigned long long *vprog = progress;
-    for (uint32_t t = warp; t < ntiles; t += UF_WARPS) {
+    // progress[item * NW + w] = (tile << 32) | steps finished, per pipeline warp
+    for (uint32_t t = gw; t < ntiles; t += NW) {
         const uint32_t k = t * 32 + lane;
         const bool valid = k < pd.nrows;
         const uint8_t *frow = src + (uint64_t)k * (len + 1);
         uint8_t *orow = dst + (uint64_t)k * len;
         uint32_t f = valid ? frow[0] : 0;
         if (f > 4) { st->fail = 1; f = 0; } // RowFilter::try_from fails -> PngError::InvalidData
+        const uint32_t m1 = f == 1 ? ~0u : 0u, m2 = f == 2 ? ~0u : 0u, m3 = f == 3 ? ~0u : 0u, m4 = f == 4 ? ~0u : 0u;
         const uint8_t *uprow = (lane == 0 && k > 0) ? orow - len : nullptr; // last row of tile t-1 (or zeros for row 0)
-        const uint32_t pw = (t + UF_WARPS - 1) % UF_WARPS;                // warp that runs tile t-1
+        const uint32_t pw = (gw + NW - 1) % NW;                            // pipeline warp that runs tile t-1
         uint32_t l0 = 0, l1 = 0, u0 = 0, u1 = 0; // left pixel (own last result), up pixel of the previous step
         for (uint32_t s0 = 0; s0 < steps; s0 += UF_CHUNK) {
             const uint32_t s1 = min(s0 + UF_CHUNK, steps);
+            // stage this lane's filtered pixels of the chunk: independent loads, one memory latency per chunk
+#pragma unroll 4
+            for (uint32_t j = 0; j < UF_CHUNK; j++) {
+                const int x = (int)(s0 + j) - (int)lane;
+                uint32_t d0 = 0, d1 = 0;
+                if (valid && x >= 0 && x < (int)npix) {
+                    d0 = ld_bytes<false>(frow + 1 + (size_t)x * bpp, n0);
+                    if (n1) d1 = ld_bytes<false>(frow + 1 + (size_t)x * bpp + 4, n1);
+                }
+                W0[j * 32 + lane] = d0;
+                if (n1) W1[j * 32 + lane] = d1;
+            }
             if (t > 0) { // lane 0 reads pixels [s0, s1) of row 32t-1: finished by tile t-1 at its step x + 32
                 const unsigned long long need = ((unsigned long long)(t - 1) << 32) | min(s1 + 31, steps);
-                while (vprog[pw] < need) {}
+                if (lane == 0) { // acquire: the boundary pixels read below were written before the progress word
+                    unsigned long long seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(progress + item * NW + pw) : "memory");
+                    } while (seen < need);
+                }
                 __syncwarp();
             }
-            for (uint32_t s = s0; s < s1; s++) {
-                // pixel above: the lane above finished it in the previous step
-                uint32_t a0 = __shfl_up_sync(0xffffffffu, l0, 1), a1 = __shfl_up_sync(0xffffffffu, l1, 1);
-                const int x = (int)s - (int)lane;
-                const bool act = valid && x >= 0 && x < (int)npix;
-                if (lane == 0) {
-                    a0 = a1 = 0;
-                    if (uprow && act) {
+            if (lane == 0) {
+#pragma unroll 4
+                for (uint32_t j = 0; j < UF_CHUNK; j++) {
+                    const uint32_t x = s0 + j;
+                    uint32_t a0 = 0, a1 = 0;
+                    if (uprow && x < npix) {
                         const uint8_t *u = uprow + (size_t)x * bpp;
                         a0 = ld_bytes<true>(u, n0);
                         if (n1) a1 = ld_bytes<true>(u + 4, n1);
                     }
+                    B0[j] = a0;
+                    B1[j] = a1;
                 }
+            }
+            __syncwarp();
+#pragma unroll 4
+            for (uint32_t s = s0; s < s1; s++) {
+                const uint32_t j = s - s0;
+                // pixel above: the lane above finished it in the previous step
+                uint32_t a0 = __shfl_up_sync(0xffffffffu, l0, 1), a1 = n1 ? __shfl_up_sync(0xffffffffu, l1, 1) : 0u;
+                const int x = (int)s - (int)lane;
+                const bool act = valid && x >= 0 && x < (int)npix;
+                if (lane == 0) { a0 = B0[j]; a1 = B1[j]; }
                 if (act) {
-                    const uint32_t d0 = ld_bytes<false>(frow + 1 + (size_t)x * bpp, n0);
-                    const uint32_t d1 = n1 ? ld_bytes<false>(frow + 1 + (size_t)x * bpp + 4, n1) : 0u;
-                    uint32_t p0, p1;
-                    switch (f) {
-                    case 0: p0 = p1 = 0; break;
-                    case 1: p0 = l0; p1 = l1; break;
-                    case 2: p0 = a0; p1 = a1; break;
-                    case 3: p0 = __vhaddu4(l0, a0); p1 = __vhaddu4(l1, a1); break;
-                    default: p0 = paeth4_u(l0, a0, u0); p1 = n1 ? paeth4_u(l1, a1, u1) : 0u; break;
-                    }
+                    const uint32_t d0 = W0[j * 32 + lane];
+                    const uint32_t d1 = n1 ? W1[j * 32 + lane] : 0u;
+                    // the rows of a tile use different filters: select by per-row masks instead of a divergent switch
+                    const uint32_t p0 = (l0 & m1) | (a0 & m2) | (__vhaddu4(l0, a0) & m3) | (paeth4(l0, a0, u0) & m4);
+                    const uint32_t p1 = n1 ? (l1 & m1) | (a1 & m2) | (__vhaddu4(l1, a1) & m3) | (paeth4(l1, a1, u1) & m4) : 0u;
                     const uint32_t r0 = __vadd4(d0, p0), r1 = __vadd4(d1, p1);
                     st_bytes(orow + (size_t)x * bpp, r0, n0);
                     if (n1) st_bytes(orow + (size_t)x * bpp + 4, r1, n1);
@@ -659,9 +690,12 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
                 }
                 u0 = a0; u1 = a1; // becomes "upleft" of the next step
             }
-            __threadfence_block(); // this chunk's pixels are visible before the progress word says so
-            __syncwarp();
-            if (lane == 0) vprog[warp] = ((unsigned long long)t << 32) | s1;
+            // only the tile's last row is read by another warp, and lane 31 wrote all of it: its release store orders
+            // those pixels before the progress word (no device-wide fence on the critical path)
+            if (lane == 31) {
+                const unsigned long long done = ((unsigned long long)t << 32) | s1;
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(progress + item * NW + gw), "l"(done) : "memory");
+            }
         }
     }
 }
@@ -1226,9 +1260,12 @@ int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, u
     }
     build_geom(h, lo, 0, &g);
     if (g.total_rows == 0) { if (out_len) *out_len = 0; return OXI_OK; }
-    Call call(filtered, len, g.data_len);
+    const size_t prog_bytes = (size_t)g.n_pass * UF_CTAS * UF_WARPS * sizeof(unsigned long long);
+    Call call(filtered, len, g.data_len, prog_bytes);
     if (!call.ok()) return call.err;
-    k_unfilter<<<g.n_pass, UF_WARPS * 32, 0, call.s->stream>>>(g, call.d_in, call.d_out, 1, len, call.st);
+    unsigned long long *prog = reinterpret_cast<unsigned long long *>(call.extra);
+    if (cudaMemsetAsync(prog, 0, prog_bytes, call.s->stream) != cudaSuccess) return fail(OXI_E_CUDA, "memset(progress)");
+    k_unfilter<<<g.n_pass * UF_CTAS, UF_WARPS * 32, 0, call.s->stream>>>(g, call.d_in, call.d_out, 1, len, call.st, prog);
     if (int rc = call.check("k_unfilter")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
