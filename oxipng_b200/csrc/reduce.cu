@@ -1265,7 +1265,18 @@ int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, u
     if (!call.ok()) return call.err;
     unsigned long long *prog = reinterpret_cast<unsigned long long *>(call.extra);
     if (cudaMemsetAsync(prog, 0, prog_bytes, call.s->stream) != cudaSuccess) return fail(OXI_E_CUDA, "memset(progress)");
-    k_unfilter<<<g.n_pass * UF_CTAS, UF_WARPS * 32, 0, call.s->stream>>>(g, call.d_in, call.d_out, 1, len, call.st, prog);
+    {
+        // the tiles of a pass wait on each other across CTAs: a cooperative launch guarantees that all of them are
+        // resident together (<= 7 x 32 CTAs of 128 threads) even when other streams keep the device busy
+        uint64_t one = 1, stride = len;
+        const uint8_t *din = call.d_in;
+        uint8_t *dout = call.d_out;
+        ScanState *sst = call.st;
+        void *args[] = {&g, &din, &dout, &one, &stride, &sst, &prog};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_unfilter, dim3(g.n_pass * UF_CTAS), dim3(UF_WARPS * 32),
+                                                    args, 0, call.s->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaLaunchCooperativeKernel(k_unfilter)");
+    }
     if (int rc = call.check("k_unfilter")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
