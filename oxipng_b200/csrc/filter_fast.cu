@@ -1,16 +1,19 @@
 // filter_fast.cu -- fast tier of PngImage::filter_image (src/png/mod.rs:355-431) for sm_100a.
 //
 // One kernel family, `k_fast<D, SC>`.  A CTA takes a *band* of consecutive scanlines of one pass of one image and
-// walks it row by row; rows are staged in a 3-slot shared-memory ring by 1-D TMA bulk copies (cp.async.bulk +
+// walks it row by row; rows are staged in a 3- or 4-slot shared-memory ring by 1-D TMA bulk copies (cp.async.bulk +
 // mbarrier) so the next row streams in while the current one is scored, and the previous row stays resident
 // (each row is read from HBM once, plus one halo row per band).  Per row:
-//   1. all five RowFilters are applied with byte-SIMD arithmetic on 128-bit shared-memory loads
-//      (src/filters/mod.rs:63-110; Paeth :242-254 in a branch-free byte form) and scored:
+//   1. all five RowFilters are applied with byte-SIMD arithmetic (src/filters/mod.rs:63-110; Paeth :242-254 in a
+//      branch-free byte form, common.cuh) and scored:
 //        MinSum  (strategies.rs:76-101)   VABSDIFF4 + accumulate: |r as i8| = 128 - ||cur-pred| - 128|
-//        Entropy (strategies.rs:105-149)  five 256-bin shared-memory histograms (x HIST_REP copies), ATOMS.ADD
-//        Bigrams (strategies.rs:153-192)  } one 65536 x u16 shared-memory counter table shared by the five trials;
-//        BigEnt  (strategies.rs:195-227)  } the thread whose add sees 0 owns the bigram, reads the final count after
-//                                           the barrier (distinct += 1, entropy += ilog2i(count)) and clears it
+//        Entropy (strategies.rs:105-149)  five 256-bin shared-memory histograms x 4 lane replicas; one prmt + one
+//                                         red.shared per residual byte
+//        Bigrams (strategies.rs:153-192)  } rows <= 16 KB: dense 32x32 tables of u32 counters per trial for windows whose
+//        BigEnt  (strategies.rs:195-227)  } two residuals lie in [-16,15] (one prmt + one red.shared per window), small
+//                                           hashes for the outliers, the None trial on coarse keys whose bounds usually
+//                                           rule it out (else an exact hash pass), branch-free table sweeps -- see
+//                                           bigram_row_small.  Longer rows: one 65536 x u16 table, trial by trial.
 //   2. the winner per strategy is picked with the reference's strict comparisons in RowFilter::ALL order
 //      (lowest filter id wins ties; all-zero rows short-circuit to None, png/mod.rs:398-404),
 //   3. only the chosen filtered row is written: recomputed in the *output-aligned* frame so that every store is a

@@ -593,7 +593,7 @@ __device__ __forceinline__ void st_bytes(uint8_t *p, uint32_t v, int n) {
 // pipeline: the warp of tile t trails the warp of tile t-1 by 32 steps, because row 32t-1 (the row above its first row)
 // is produced by lane 31 of that warp.  Progress is published per warp in global memory every UF_CHUNK steps (the
 // pipeline spans SMs: one SM alone is bound by instruction issue, ~140 instructions per warp and step); the boundary row
-// goes through global memory as well (stores are fenced at device scope before the progress word is updated, the reader
+// goes through global memory as well (release store of the progress word by the lane that wrote it, the reader
 // bypasses L1 with ld.global.cg).  All CTAs of a launch are resident at once (grid <= 7 x 32 CTAs of 128 threads), so
 // waiting on an earlier tile cannot deadlock.
 // Memory latency stays off the step-to-step dependency chain: at the start of a chunk every lane fetches the filtered
