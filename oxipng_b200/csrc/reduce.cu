@@ -601,6 +601,9 @@ __device__ __forceinline__ void st_bytes(uint8_t *p, uint32_t v, int n) {
 // per-warp shared-memory stage laid out [step][lane] (conflict-free), and the steps then read shared memory only.
 constexpr int UF_WARPS = 4, UF_CTAS = 32, UF_CHUNK = 32;
 constexpr uint32_t UF_STAGE_WORDS = 2 * UF_CHUNK * 32 + 2 * UF_CHUNK; // per warp: W0,W1[step][lane], B0,B1[step]
+// BPP = 4: specialisation for 4-byte pixels (RGBA8, gray+alpha 16): one word per pixel, no byte-count arithmetic in the
+// step (the generic body is ~290 instructions per step, all executed by a lone warp per scheduler); BPP = 0: any bpp.
+template <int BPP>
 __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_t *__restrict__ in, uint8_t *out,
                                                             uint64_t n_images, uint64_t in_stride, ScanState *st,
                                                             unsigned long long *progress) {
@@ -612,7 +615,7 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
     const uint32_t gw = (blockIdx.x % UF_CTAS) * UF_WARPS + warp, NW = UF_CTAS * UF_WARPS; // warp of the item's pipeline
     const uint64_t img = item / g.n_pass;
     const PassDesc pd = g.pass[item % g.n_pass];
-    const int bpp = (int)g.bpp, n0 = bpp < 4 ? bpp : 4, n1 = bpp - n0; // pixel = word0 (n0 bytes) + word1 (n1 bytes)
+    const int bpp = BPP ? BPP : (int)g.bpp, n0 = bpp < 4 ? bpp : 4, n1 = bpp - n0; // pixel = word0 (n0 bytes) + word1 (n1 bytes)
     const uint32_t len = pd.len, npix = len / bpp;
     // filtered stream: row r of the image starts at in_base + r (one filter byte per earlier row), then 1 + len bytes
     const uint8_t *src = in + img * in_stride + pd.in_base + pd.row0;
@@ -633,7 +636,7 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
         for (uint32_t s0 = 0; s0 < steps; s0 += UF_CHUNK) {
             const uint32_t s1 = min(s0 + UF_CHUNK, steps);
             // stage this lane's filtered pixels of the chunk: independent loads, one memory latency per chunk
-#pragma unroll 4
+#pragma unroll 16
             for (uint32_t j = 0; j < UF_CHUNK; j++) {
                 const int x = (int)(s0 + j) - (int)lane;
                 uint32_t d0 = 0, d1 = 0;
@@ -655,7 +658,7 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
                 __syncwarp();
             }
             if (lane == 0) {
-#pragma unroll 4
+#pragma unroll 16
                 for (uint32_t j = 0; j < UF_CHUNK; j++) {
                     const uint32_t x = s0 + j;
                     uint32_t a0 = 0, a1 = 0;
@@ -1273,7 +1276,8 @@ int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, u
         uint8_t *dout = call.d_out;
         ScanState *sst = call.st;
         void *args[] = {&g, &din, &dout, &one, &stride, &sst, &prog};
-        cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_unfilter, dim3(g.n_pass * UF_CTAS), dim3(UF_WARPS * 32),
+        const void *fn = g.bpp == 4 ? (const void *)k_unfilter<4> : (const void *)k_unfilter<0>;
+        cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(g.n_pass * UF_CTAS), dim3(UF_WARPS * 32),
                                                     args, 0, call.s->stream);
         if (e != cudaSuccess) return fail_cuda(e, "cudaLaunchCooperativeKernel(k_unfilter)");
     }
