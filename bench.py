@@ -381,12 +381,18 @@ def run_other_configs(ox, synth, torch, dev, local, stream, args):
         ("c2_basic_none_rgb8_8192", 8192, 8192, 3, 8, False, [ox.FilterStrategy.NONE]),
         ("c3a_bigrams_rgba16_4096", 4096, 4096, 4, 16, False, [ox.FilterStrategy.Bigrams]),
         ("c3a_bigent_rgba16_4096", 4096, 4096, 4, 16, False, [ox.FilterStrategy.BigEnt]),
+        ("c3b_bigrams_bigent_rgba8_4096_adam7", 4096, 4096, 4, 8, True, [ox.FilterStrategy.Bigrams, ox.FilterStrategy.BigEnt]),
+        ("bigrams_bigent_rgba8_4096", 4096, 4096, 4, 8, False, [ox.FilterStrategy.Bigrams, ox.FilterStrategy.BigEnt]),
     ]
     for name, w, h, ch, bd, il, strat in cfgs:
         ct = {1: ox.ColorType.Grayscale(), 3: ox.ColorType.RGB(), 4: ox.ColorType.RGBA()}[ch]
         hdr = ox.IhdrData(w, h, ct, ox.BitDepth(bd), il)
         d = synth.photo_image(w, h, ch, bd, 0xB2000001, dev)
-        n, rows = d.numel(), h
+        if il:  # the same picture in the Adam7 layout (oxi_interlace_image, interlace.rs:6-60)
+            prog = ox.PngImage(ox.IhdrData(w, h, ct, ox.BitDepth(bd), False), d.cpu().numpy())
+            d = torch.from_numpy(ox.interlace_image(prog).data.copy()).to(dev)
+        n = d.numel()
+        rows = int(ox.lib().oxi_num_scanlines(__import__("ctypes").byref(hdr._c()), n))
         o = [torch.empty(n + rows, dtype=torch.uint8, device=dev) for _ in strat]
         u = [torch.empty(rows, dtype=torch.uint8, device=dev) for _ in strat]
 
