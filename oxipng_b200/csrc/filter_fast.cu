@@ -511,9 +511,6 @@ __device__ __forceinline__ bool ohash_add(uint32_t *h, uint32_t key) {
     }
     return false;
 }
-__device__ __forceinline__ uint32_t range_code4(uint32_t r) { // per byte: (b + 16) mod 256 (no carries across bytes)
-    return ((r & 0x7F7F7F7Fu) + 0x10101010u) ^ (r & 0x80808080u);
-}
 // the next row of the band, streamed into its ring slot (by TMA, or cooperatively for rows TMA cannot take)
 struct Prefetch {
     bool on, tma;
@@ -704,8 +701,6 @@ template <int D, int NT>
 __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
                                                      const Smem &sm, uint32_t h0_slots, const Prefetch &pf) {
     const uint32_t nwords = (len + 3) >> 2, npairs = (nwords + 1) >> 1;
-    uint32_t *h0 = sm.table;
-    const uint32_t hmask = h0_slots - 1, hshift = (uint32_t)__clz((int)h0_slots) + 1; // flagged path (h0_add)
     const uint32_t lane = threadIdx.x & 31u, rep = (lane >> 2) & 1u;
     const uint32_t dense_base = smem_u32(sm.small);
     const uint32_t c1 = rep * 0x10101010u, c2 = rep * 0x80808080u;
