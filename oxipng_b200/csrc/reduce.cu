@@ -307,7 +307,12 @@ __global__ void __launch_bounds__(RT) k_collect_colors(const uint8_t *__restrict
                 cur = atomicCAS(&l_key[s], 0ull, tagged);
                 if (cur == 0) { atomicAdd(&l_count, 1u); cur = tagged; }
             }
-            if (cur == tagged) { atomicMin(&l_first[s], (unsigned long long)i); break; }
+            if (cur == tagged) {
+                // first[] only ever decreases and a thread's pixels come in increasing order: after the first occurrence
+                // the (64-bit, CAS-emulated) shared atomic is almost never needed
+                if ((unsigned long long)i < *(volatile unsigned long long *)&l_first[s]) atomicMin(&l_first[s], (unsigned long long)i);
+                break;
+            }
             s = (s + 1) & (LSLOTS - 1);
             if (l_count > 256) break;
         }

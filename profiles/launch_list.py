@@ -12,5 +12,5 @@ for r in rows[1:]:
     a = agg.setdefault(r[ci["Kernel Name"]], [0, 0.0]); a[0] += 1; a[1] += v
 tot = sum(a[1] for a in agg.values())
 print("launches   total ms   share  kernel")
-for k, a in sorted(agg.items(), key=lambda t: -t[1][1])[:12]:
+for k, a in sorted(agg.items(), key=lambda t: -t[1][1])[:int(sys.argv[2]) if len(sys.argv) > 2 else 12]:
     print(f"{a[0]:8d} {a[1]:10.3f} {100 * a[1] / tot:6.1f}%  {k[:100]}")
