@@ -174,18 +174,23 @@ __device__ __forceinline__ uint32_t min_bits_of(uint32_t b) {
     if (b == (b & 15u) * 0x11u) return 4;
     return 8;
 }
+// Word-parallel form: a byte has period d iff bit i equals bit i+d for every i, i.e. ((b >> d) ^ b) has no bit set
+// among its low 8-d bits; period 1 implies 2 implies 4, so three OR-accumulators give the maximum over all bytes.
 __global__ void __launch_bounds__(RT) k_min_bits(const uint8_t *__restrict__ in, uint64_t n, ScanState *st) {
-    uint32_t m = 1;
+    uint32_t n8 = 0, n4 = 0, n2 = 0; // some byte is not 4- / 2- / 1-periodic
     const uint64_t n16 = n / 16, stride = (uint64_t)gridDim.x * RT;
     const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
     for (uint64_t i = (uint64_t)blockIdx.x * RT + threadIdx.x; i < n16; i += stride) {
         const uint4 v = in4[i];
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) m = max(m, min_bits_of((w[k] >> (8 * j)) & 255u));
+        for (int k = 0; k < 4; k++) {
+            n8 |= ((w[k] >> 4) ^ w[k]) & 0x0F0F0F0Fu;
+            n4 |= ((w[k] >> 2) ^ w[k]) & 0x3F3F3F3Fu;
+            n2 |= ((w[k] >> 1) ^ w[k]) & 0x7F7F7F7Fu;
+        }
     }
+    uint32_t m = n8 ? 8u : n4 ? 4u : n2 ? 2u : 1u;
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (uint64_t i = n16 * 16; i < n; i++) m = max(m, min_bits_of(in[i]));
 #pragma unroll
@@ -1060,7 +1065,7 @@ int oxi_used_histogram256(const uint8_t *data, size_t len, uint64_t hist[256]) {
     if (!data || !hist) return fail(OXI_E_ARG, "bad arguments");
     Call call(data, len, 0);
     if (!call.ok()) return call.err;
-    k_hist256<<<grid_for((len + 15) / 16, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, len, call.st);
+    k_hist256<<<grid_for((len + 15) / 16, call.c->num_sms, 2), RT, 0, call.s->stream>>>(call.d_in, len, call.st);
     if (int rc = call.check("k_hist256")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
@@ -1095,7 +1100,7 @@ int oxi_reduced_palette(const oxi_ihdr *h, const oxi_color_aux *aux, const uint8
     if (h->bit_depth != 8 || h->color_type != 3 || !aux) return OXI_NONE; // palette.rs:13-18
     Call call(data, len, len, 256);
     if (!call.ok()) return call.err;
-    k_hist256<<<grid_for((len + 15) / 16, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, len, call.st);
+    k_hist256<<<grid_for((len + 15) / 16, call.c->num_sms, 2), RT, 0, call.s->stream>>>(call.d_in, len, call.st);
     if (int rc = call.check("k_hist256")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
