@@ -1,25 +1,13 @@
 // Exhaustive device check of the byte-SIMD Paeth predictor used by the fast tier against the scalar definition
 // (src/filters/mod.rs:242-254): all 2^24 (a,b,c), each placed in every byte lane with different neighbours.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o paeth4_exhaustive paeth4_exhaustive.cu
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o paeth4_exhaustive paeth4_exhaustive.cu
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
 
-__device__ __forceinline__ uint32_t signmask4(uint32_t x) { // 0xFF in every byte whose MSB is set
-    uint32_t d;                                             // (prmt's sign-replicate selectors; __byte_perm masks them off)
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xba98u));
-    return d;
-}
-__device__ __forceinline__ uint32_t sel4(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
-__device__ __forceinline__ uint32_t paeth4(uint32_t a, uint32_t b, uint32_t c) {
-    const uint32_t pa = __vabsdiffu4(b, c), pb = __vabsdiffu4(a, c);
-    const uint32_t pd = __vabsdiffu4(pa, pb);
-    const uint32_t pc = pd | __vcmpeq4(pd, __vabsdiffu4(a, b));
-    const uint32_t le = __vcmpleu4(pa, pb);
-    const uint32_t w = sel4(le, a, b), mn = sel4(le, pa, pb);
-    const uint32_t t = (pc | 0x80808080u) - mn;
-    return sel4(signmask4(t | pc), w, c);
-}
+#include "../../oxipng_b200/csrc/common.cuh" // the product's own paeth4
+using oxi::paeth4;
+
 __device__ uint32_t paeth1(uint32_t a, uint32_t b, uint32_t c) {
     int p = (int)a + (int)b - (int)c;
     int pa = abs(p - (int)a), pb = abs(p - (int)b), pc = abs(p - (int)c);
