@@ -243,6 +243,23 @@ def test_randomised_shapes_fast_tier():
                    label=f"rnd-all/{it}/{w}x{h}/{ct}/{bd}/{kind}")
 
 
+def test_paeth4_exhaustive_on_device():
+    """The byte-SIMD Paeth predictor (common.cuh) against the scalar definition for all 2^24 (a, b, c) in every byte lane:
+    builds tests/cuda/paeth4_exhaustive.cu with nvcc and runs it."""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda")
+    exe = os.path.join(here, "paeth4_exhaustive")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-o", exe,
+                           os.path.join(here, "paeth4_exhaustive.cu")], stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "mismatches=0" in out.stdout, out.stdout + out.stderr
+
+
 def test_fast_tier_batch_many_images():
     import oxipng_b200 as ox
     n = 37
