@@ -279,6 +279,8 @@ struct ColorTable {
 };
 __device__ __forceinline__ uint32_t hash_color(uint32_t key) { return (key * 2654435761u) ^ (key >> 15); }
 __device__ __forceinline__ uint32_t load_key(const uint8_t *px, uint32_t ch) {
+    if (ch == 4 && (reinterpret_cast<uintptr_t>(px) & 3u) == 0) return *reinterpret_cast<const uint32_t *>(px); // RGBA8
+    if (ch == 2 && (reinterpret_cast<uintptr_t>(px) & 1u) == 0) return *reinterpret_cast<const uint16_t *>(px); // GA8
     uint32_t k = px[0];
     if (ch > 1) k |= (uint32_t)px[1] << 8;
     if (ch > 2) k |= (uint32_t)px[2] << 16;
