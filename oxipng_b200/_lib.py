@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liboxipng_b200.so")
+# OXIPNG_B200_LIB: another build of the same library (A/B timing of kernel variants, profiles/ab.py); still the CUDA path
+LIB_PATH = os.environ.get("OXIPNG_B200_LIB") or os.path.join(HERE, "liboxipng_b200.so")
 
 OXI_OK, OXI_NONE = 0, 1
 FLAG_FORCE_GENERIC, FLAG_FORCE_FAST = 1, 2

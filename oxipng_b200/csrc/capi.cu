@@ -19,6 +19,7 @@ void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxe
 
 thread_local std::string t_err;
 thread_local int t_device = 0;
+thread_local const DevIO *t_devio = nullptr;
 
 int fail(int code, const char *msg) {
     t_err = msg;
@@ -125,10 +126,16 @@ DeviceCtx *get_ctx(int device, int *err) {
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { *err = fail_cuda(e, "cudaGetDeviceProperties"); return nullptr; }
-    if (prop.major < 10) { *err = fail(OXI_E_CUDA, "device is not sm_100 class"); return nullptr; }
+    // the library holds sm_100a code only (arch-specific targets embed no PTX and are not forward compatible)
+    if (prop.major != 10 || prop.minor != 0) {
+        *err = fail(OXI_E_UNSUPPORTED, "device is not sm_100 (B200): this build has no kernel image for it");
+        return nullptr;
+    }
     DeviceCtx *c = new DeviceCtx;
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
+    e = fast_tier_init(device, &c->smem_window);
+    if (e != cudaSuccess) { delete c; *err = fail_cuda(e, "fast_tier_init"); return nullptr; }
     g_ctx[device] = c;
     return c;
 }
@@ -163,22 +170,41 @@ Slot *acquire_slot(DeviceCtx *c) {
     }
     Slot *s = new Slot;
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return nullptr; }
+    if (cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaStreamDestroy(s->stream);
+        delete s;
+        return nullptr;
+    }
     s->own_stream = true;
     return s;
 }
-void release_slot(DeviceCtx *c, Slot *s) {
-    std::lock_guard<std::mutex> lk(c->mu);
-    c->free_slots.push_back(s);
+// Slots are pooled, so their number is bounded by the peak number of concurrent calls on the device; beyond
+// MAX_POOLED idle slots a returned slot is destroyed instead (its buffers are freed).
+constexpr size_t MAX_POOLED = 64;
+static void destroy_slot(Slot *s) {
+    cudaStreamSynchronize(s->stream);
+    if (s->ev_pending) cudaEventSynchronize(s->ev);
+    cudaFree(s->scratch); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_pre);
+    cudaEventDestroy(s->ev);
+    cudaStreamDestroy(s->stream);
+    delete s;
 }
-// Slot bound to a caller stream (device-resident API): scratch reuse is then ordered by that stream.
-Slot *stream_slot(DeviceCtx *c, cudaStream_t st) {
-    std::lock_guard<std::mutex> lk(c->mu);
-    auto it = c->stream_slots.find(st);
-    if (it != c->stream_slots.end()) return it->second;
-    Slot *s = new Slot;
-    s->stream = st;
-    c->stream_slots[st] = s;
-    return s;
+void release_slot(DeviceCtx *c, Slot *s) {
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (c->free_slots.size() < MAX_POOLED) { c->free_slots.push_back(s); return; }
+    }
+    destroy_slot(s);
+}
+cudaError_t slot_begin(Slot *s, cudaStream_t st) {
+    if (!s->ev_pending) return cudaSuccess;
+    s->ev_pending = false;
+    return cudaStreamWaitEvent(st, s->ev, 0);
+}
+void release_slot_async(DeviceCtx *c, Slot *s, cudaStream_t st) {
+    if (cudaEventRecord(s->ev, st) == cudaSuccess) s->ev_pending = true;
+    else cudaStreamSynchronize(st);
+    release_slot(c, s);
 }
 
 // ---- dispatch -----------------------------------------------------------------------------------------------
@@ -196,8 +222,8 @@ bool valid_strategy(const oxi_strategy *s) {
 }
 
 // Upload Predefined lists (stream ordered) and fill the kernel-side strategy set.
-int make_set(Slot *slot, const oxi_strategy *st, size_t k, uint8_t *const *d_outs, uint8_t *const *d_used,
-             StrategySet *set) {
+int make_set(Slot *slot, cudaStream_t stream, const oxi_strategy *st, size_t k, uint8_t *const *d_outs,
+             uint8_t *const *d_used, StrategySet *set) {
     if (k == 0 || k > (size_t)MAX_STRATEGIES) return fail(OXI_E_ARG, "strategy count must be 1..12");
     size_t pre_total = 0;
     for (size_t j = 0; j < k; j++) {
@@ -218,7 +244,7 @@ int make_set(Slot *slot, const oxi_strategy *st, size_t k, uint8_t *const *d_out
         d.n_predefined = 0;
         if (st[j].kind == OXI_PREDEFINED && st[j].n_predefined) {
             size_t n = st[j].n_predefined > 0xFFFFFFFFu ? 0xFFFFFFFFu : st[j].n_predefined;
-            cudaError_t e = cudaMemcpyAsync(slot->d_pre + off, st[j].predefined, n, cudaMemcpyHostToDevice, slot->stream);
+            cudaError_t e = cudaMemcpyAsync(slot->d_pre + off, st[j].predefined, n, cudaMemcpyHostToDevice, stream);
             if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(predefined)");
             d.predefined = slot->d_pre + off;
             d.n_predefined = (uint32_t)n;
@@ -230,20 +256,21 @@ int make_set(Slot *slot, const oxi_strategy *st, size_t k, uint8_t *const *d_out
     return OXI_OK;
 }
 
-bool want_fast(const Geom &g, const StrategySet &set, unsigned flags) {
+bool want_fast(const DeviceCtx *c, const Geom &g, const StrategySet &set, unsigned flags) {
     if (flags & OXI_FLAG_FORCE_GENERIC) return false;
-    return fast_supported(g, set);
+    return fast_tier_usable(c->smem_window) && fast_supported(g, set);
 }
 
-int run_filters(DeviceCtx *c, Slot *slot, const Geom &g, const uint8_t *d_data, size_t n_images, const StrategySet &set,
-                unsigned flags) {
+int run_filters(DeviceCtx *c, Slot *slot, cudaStream_t stream, const Geom &g, const uint8_t *d_data, size_t n_images,
+                const StrategySet &set, unsigned flags) {
     if (g.total_rows == 0 || n_images == 0) return OXI_OK;
     LaunchCtx lc;
     lc.device = c->device;
-    lc.stream = slot->stream;
+    lc.stream = stream;
+    lc.smem_window = c->smem_window;
     lc.num_sms = c->num_sms;
     cudaError_t e;
-    if (want_fast(g, set, flags)) {
+    if (want_fast(c, g, set, flags)) {
         lc.scratch = nullptr;
         lc.scratch_bytes = 0;
         e = launch_fast(lc, g, d_data, n_images, set);
@@ -277,7 +304,7 @@ int filter_host_chunk(DeviceCtx *c, Slot *slot, const Geom &g, const uint8_t *da
         d_used[j] = d_outs[j] + out_stride;
     }
     StrategySet set;
-    int rc = make_set(slot, st, k, d_outs, d_used, &set);
+    int rc = make_set(slot, slot->stream, st, k, d_outs, d_used, &set);
     if (rc) return rc;
     if (stride_in == g.data_len) {
         e = cudaMemcpyAsync(slot->d_in, data, n_images * (size_t)g.data_len, cudaMemcpyHostToDevice, slot->stream);
@@ -286,7 +313,7 @@ int filter_host_chunk(DeviceCtx *c, Slot *slot, const Geom &g, const uint8_t *da
                               slot->stream);
     }
     if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(H2D)");
-    rc = run_filters(c, slot, g, slot->d_in, n_images, set, flags);
+    rc = run_filters(c, slot, slot->stream, g, slot->d_in, n_images, set, flags);
     if (rc) return rc;
     for (size_t j = 0; j < k; j++) {
         if (outs && outs[j]) {
@@ -385,7 +412,7 @@ const char *oxi_filter_tier(const oxi_ihdr *h, size_t data_len, const oxi_strate
     set.k = 1;
     set.s[0].kind = st->kind;
     set.s[0].basic = st->basic_filter;
-    return fast_supported(g, set) ? "fast" : "generic";
+    return fast_supported(g, set) ? "fast" : "generic"; // (a device whose shared-memory window differs runs generic)
 }
 
 int oxi_filter_batch_device(int device, void *stream, const oxi_ihdr *h, const uint8_t *d_data, size_t data_len,
@@ -400,11 +427,19 @@ int oxi_filter_batch_device(int device, void *stream, const oxi_ihdr *h, const u
     if (!c) return err;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
-    Slot *slot = stream_slot(c, (cudaStream_t)stream);
+    // scratch (Predefined lists, generic-tier rows) comes from a pooled slot; the work runs on the caller's stream and
+    // the slot goes back with an event, so nothing is shared between concurrent callers and nothing synchronises
+    Slot *slot = acquire_slot(c);
+    if (!slot) return fail(OXI_E_CUDA, "cannot create stream");
+    const cudaStream_t st = (cudaStream_t)stream;
     StrategySet set;
-    int rc = make_set(slot, strategies, k, d_outs, d_filters_used, &set);
-    if (rc) return rc;
-    return run_filters(c, slot, g, d_data, n_images, set, flags);
+    int rc = OXI_OK;
+    e = slot_begin(slot, st);
+    if (e != cudaSuccess) rc = fail_cuda(e, "cudaStreamWaitEvent");
+    if (rc == OXI_OK) rc = make_set(slot, st, strategies, k, d_outs, d_filters_used, &set);
+    if (rc == OXI_OK) rc = run_filters(c, slot, st, g, d_data, n_images, set, flags);
+    release_slot_async(c, slot, st);
+    return rc;
 }
 
 int oxi_filter_batch(const oxi_ihdr *h, const uint8_t *data, size_t data_len, size_t n_images,
@@ -413,6 +448,10 @@ int oxi_filter_batch(const oxi_ihdr *h, const uint8_t *data, size_t data_len, si
     Geom g;
     if (!build_geom(h, data_len, optimize_alpha, &g)) return fail(OXI_E_ARG, "invalid IHDR");
     if (!data || !strategies || k == 0 || k > (size_t)MAX_STRATEGIES) return fail(OXI_E_ARG, "bad arguments");
+    // a single image may carry trailing bytes that hold no further scanline (the reference's iterator ignores them);
+    // in a batch the images sit data_len apart, so data_len must be exactly the scanlines of one image
+    if (n_images > 1 && g.data_len != data_len)
+        return fail(OXI_E_ARG, "data_len is not a whole number of scanlines for this IHDR");
     int err = 0;
     DeviceCtx *c = get_ctx(t_device, &err);
     if (!c) return err;
@@ -430,7 +469,9 @@ int oxi_filter_batch(const oxi_ihdr *h, const uint8_t *data, size_t data_len, si
     int rc = OXI_OK;
     for (int i = 0; i < NS; i++) {
         slots[i] = acquire_slot(c);
-        if (!slots[i]) rc = fail(OXI_E_CUDA, "cannot create stream");
+        if (!slots[i]) { rc = fail(OXI_E_CUDA, "cannot create stream"); continue; }
+        e = slot_begin(slots[i], slots[i]->stream);
+        if (e != cudaSuccess) rc = fail_cuda(e, "cudaStreamWaitEvent");
     }
     for (size_t ci = 0; ci < n_chunks && rc == OXI_OK; ci++) {
         Slot *s = slots[ci % NS];

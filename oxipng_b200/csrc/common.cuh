@@ -128,6 +128,7 @@ struct LaunchCtx {
     int device;
     cudaStream_t stream;
     int num_sms;
+    uint32_t smem_window; // DeviceCtx::smem_window
     // scratch provided by the caller (capi.cu) for the generic tier
     uint8_t *scratch;
     size_t scratch_bytes;
@@ -140,6 +141,10 @@ cudaError_t launch_generic(const LaunchCtx &ctx, const Geom &g, const uint8_t *d
 
 // fast tier (filter_fast.cu): alpha_bytes == 0, rows that fit the shared-memory staging ring.
 bool fast_supported(const Geom &g, const StrategySet &set);
+// once per device: raises the dynamic shared-memory limit of every k_fast instantiation to the full 227 KB (so no
+// launch ever changes a function attribute) and probes the shared-window address of dynamic shared memory
+cudaError_t fast_tier_init(int device, uint32_t *smem_window);
+bool fast_tier_usable(uint32_t smem_window);
 cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_data, size_t n_images,
                         const StrategySet &set);
 

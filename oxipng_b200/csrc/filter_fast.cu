@@ -87,6 +87,15 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 __device__ __forceinline__ void smem_inc(uint32_t addr) { // no-return add of 1 on a shared-window byte address
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
 }
+// The same with the table's shared-window address as an immediate of the instruction (ATOMS [R + imm]).  The dynamic
+// shared memory of a kernel without static shared memory that is not launched in a cluster starts at shared-window
+// address SMEM_WIN on sm_100 (the first KB of the window is the system's); k_fast checks it at entry and traps otherwise,
+// so a different driver layout fails loudly instead of counting in the wrong place.
+constexpr uint32_t SMEM_WIN = 0x400;
+template <uint32_t IMM>
+__device__ __forceinline__ void smem_inc_at(uint32_t off) {
+    asm volatile("red.shared.add.u32 [%0+%1], %2;" ::"r"(off), "n"(IMM), "r"(1u) : "memory");
+}
 template <int F>
 __device__ __forceinline__ uint32_t pred4(uint32_t left, uint32_t up, uint32_t ul) {
     if (F == 0) return 0u;
@@ -537,71 +546,99 @@ __device__ __forceinline__ void issue_prefetch(const Prefetch &pf) {
 // ilog2i that is also valid for i == 0 (returns 0): no branch in the table sweeps.  PTX shl clamps the shift amount,
 // so for i == 0 (lg = -1) the subtrahend is 0 and the product is 0 * 1.
 __device__ __forceinline__ uint32_t ilog2i_z(uint32_t i) {
-    const uint32_t lg = 31u - (uint32_t)__clz((int)i);
-    uint32_t sh;
+    uint32_t lg, sh; // bfind: position of the most significant set bit, 0xFFFFFFFF for 0 (SASS FLO)
+    asm("bfind.u32 %0, %1;" : "=r"(lg) : "r"(i));
     asm("shl.b32 %0, %1, %2;" : "=r"(sh) : "r"(2u), "r"(lg));
     return i * (lg + 2u) - sh;
 }
-// Dense tables, trials 1..4: u32 counters, two lane-selected replicas per trial, 32 KB in all.  Byte offset of the
-// counter of window (first, second) -- both as range codes 0..31 -- of trial f in replica rep:
-//     first << 10 | (f-1) << 8 | rep << 7 | (second ^ first ^ 16*rep) << 2
-// i.e. the high byte of the offset is (first << 2 | f-1) and the low byte (swizzled second << 2 | rep << 7): one prmt
-// per window picks the two bytes out of two pre-scaled words, one red.shared per window counts it.  The bank is
-// second ^ first (^ 16 for replica 1), so runs like "(x, alpha residual 0)" spread over the banks.
-__device__ __forceinline__ uint32_t dense_off(uint32_t f, uint32_t rep, uint32_t first, uint32_t second) {
-    return (first << 10) | ((f - 1u) << 8) | (rep << 7) | ((second ^ first ^ (rep << 4)) << 2);
+// Dense tables, trials 1..4: u32 counters, 16 KB in all.  Byte offset of the counter of window (first, second) -- both as
+// range codes 0..31 -- of trial f:
+//     first << 9 | (f-1) << 7 | ((second + 5 * first) & 31) << 2
+// i.e. the high byte of the offset is (first << 1 | (f-1) >> 1) and the low byte ((f-1) & 1) << 7 | bank << 2: one prmt
+// per window picks the two bytes out of two pre-scaled words, one red.shared per window counts it (the hardware
+// merges the lanes of one instruction that hit the same counter: SASS ATOMS.POPC.INC).  The bank is second + 5 * first:
+// the keys of a filtered photographic row form a cluster of a few residuals around (16, 16), and a 5 x 5 (6 x 5) block
+// of neighbouring keys lands on distinct banks, where first ^ second folds all "equal residual" keys onto one bank.
+// Lane-selected replicas and a per-lane rotation of the windows were measured in round 1 at 3.1 wavefronts per ATOMS;
+// replaying the kernel's lane -> window map on the bench images (profiles/r02_bank_sim.py) gives 3.06 for that layout
+// and 1.85 for this one, because the lanes of one instruction then count the same channel pair and mostly coincide.
+constexpr uint32_t COARSE_OFF = 16384; // byte offset of the coarse table of trial 0 behind the dense tables
+__device__ __forceinline__ uint32_t dense_off(uint32_t f, uint32_t first, uint32_t second) {
+    return (first << 9) | ((f - 1u) << 7) | (((second + 5u * first) & 31u) << 2);
 }
 
-// One row word (four windows) of trials 1..4.  tr = range codes of the word's residual bytes, tpr = codes of the stream
-// bytes in front of them -- both with their bytes rotated by the lane's window rotation (every step is bytewise, so the
-// rotation only changes which window a given red.shared of the warp counts).
-template <int F>
-__device__ __forceinline__ void dense_word(uint32_t tr, uint32_t tpr, uint32_t dense_base, uint32_t c1, uint32_t c2) {
-    const uint32_t hi = tpr * 4u + (uint32_t)(F - 1) * 0x01010101u;
-    const uint32_t lo = (tr ^ tpr ^ c1) * 4u + c2; // c1 = rep * 0x10101010, c2 = rep * 0x80808080
-    smem_inc(dense_base + prmt(lo, hi, 0xCC40u));
-    smem_inc(dense_base + prmt(lo, hi, 0xDD51u));
-    smem_inc(dense_base + prmt(lo, hi, 0xEE62u));
-    smem_inc(dense_base + prmt(lo, hi, 0xFF73u));
+// One complete row word (four windows) of trial F.  t = range codes of the word's residual bytes, tpw = codes of the
+// stream bytes in front of them; all eight codes < 32.  DB = shared-window address of the dense tables.
+template <int F, uint32_t DB>
+__device__ __forceinline__ void dense_word(uint32_t t, uint32_t tpw) {
+    const uint32_t hi = tpw * 2u + (uint32_t)((F - 1) >> 1) * 0x01010101u;
+    const uint32_t s = tpw * 5u + t; // bytes <= 31 + 155: no carry between bytes; << 2 moves only bits the mask drops
+    const uint32_t lo = ((s << 2) & 0x7C7C7C7Cu) | ((uint32_t)((F - 1) & 1) * 0x80808080u);
+    smem_inc_at<DB>(prmt(lo, hi, 0xCC40u));
+    smem_inc_at<DB>(prmt(lo, hi, 0xDD51u));
+    smem_inc_at<DB>(prmt(lo, hi, 0xEE62u));
+    smem_inc_at<DB>(prmt(lo, hi, 0xFF73u));
 }
-// the same word window by window: tail words and words with an out-of-range byte (t, tprev unrotated)
-// (one copy for all trials, F at run time: this path is off the straight line and should stay small in the i-cache)
-__device__ __noinline__ void dense_word_slow(uint32_t F, uint32_t t, uint32_t tprev, int valid, uint32_t dense_base,
-                                             uint32_t rep, uint32_t *ohash, uint32_t *s_out) {
+// the same word window by window: tail words and words with an out-of-range byte
+// (one copy for all trials, F at run time: this path is off the straight line and should stay small in the i-cache;
+// it takes shared-window addresses, not pointers, so that the callers form no generic pointers on the straight line)
+template <uint32_t DB>
+__device__ __noinline__ void dense_word_slow(uint32_t F, uint32_t t, uint32_t tprev, int valid, uint32_t s_out_addr) {
+    uint32_t *ohash = reinterpret_cast<uint32_t *>(__cvta_shared_to_generic(DB + DENSE_WORDS * 4u));
+    volatile uint32_t *s_out = reinterpret_cast<volatile uint32_t *>(__cvta_shared_to_generic(s_out_addr));
     uint32_t tp = tprev >> 24;
     for (int j = 0; j < 4; j++) {
         const uint32_t tj = (t >> (8 * j)) & 255u;
         if (j < valid) {
             if (((tp | tj) & 0xE0u) == 0) {
-                smem_inc(dense_base + dense_off(F, rep, tp, tj));
-            } else if (*(volatile uint32_t *)&s_out[F] == 0) {
+                smem_inc(DB + dense_off(F, tp, tj));
+            } else if (s_out[F] == 0) {
                 // outliers go to the trial's hash table until an insert finds it crowded; from then on the
                 // trial is flagged and all its outliers are counted in h0 after the barrier
                 if (!ohash_add(ohash + (F - 1) * HSLOTS, (((tp + 240u) & 255u) << 8) | ((tj + 240u) & 255u)))
-                    *(volatile uint32_t *)&s_out[F] = 1u;
+                    s_out[F] = 1u;
             }
         }
         tp = tj;
     }
 }
 
-// trial 0 on coarse keys (low five bits of both raw bytes): one table of 32x32 counters (the keys of raw rows are
-// spread widely, a second replica buys little) in the 4 KB behind the tables of trials 1..4; offset
-// first << 7 | (second ^ first) << 2, i.e. high byte first >> 1, low byte (first & 1) << 7 | swizzled second << 2
-__device__ __forceinline__ void dense_word0(uint32_t xr, uint32_t pr, uint32_t dense_base) {
-    const uint32_t hi = (pr >> 1) & 0x0F0F0F0Fu;
-    const uint32_t lo = (pr & 0x01010101u) * 128u + ((xr ^ pr) & 0x1F1F1F1Fu) * 4u;
-    smem_inc(dense_base + 32768u + prmt(lo, hi, 0xCC40u));
-    smem_inc(dense_base + 32768u + prmt(lo, hi, 0xDD51u));
-    smem_inc(dense_base + 32768u + prmt(lo, hi, 0xEE62u));
-    smem_inc(dense_base + 32768u + prmt(lo, hi, 0xFF73u));
+// trial 0 on coarse keys (low five bits of both raw bytes): 32x32 counters in the even 128-byte lines of the 8 KB at
+// COARSE_OFF; offset first << 8 | ((second ^ first) & 31) << 2, i.e. high byte = first, low byte = bank << 2
+template <uint32_t DB>
+__device__ __forceinline__ void dense_word0(uint32_t x, uint32_t xpw) {
+    const uint32_t hi = xpw & 0x1F1F1F1Fu;
+    const uint32_t lo = ((x ^ xpw) & 0x1F1F1F1Fu) << 2;
+    smem_inc_at<DB + COARSE_OFF>(prmt(lo, hi, 0xCC40u));
+    smem_inc_at<DB + COARSE_OFF>(prmt(lo, hi, 0xDD51u));
+    smem_inc_at<DB + COARSE_OFF>(prmt(lo, hi, 0xEE62u));
+    smem_inc_at<DB + COARSE_OFF>(prmt(lo, hi, 0xFF73u));
 }
-__device__ __noinline__ void dense_word0_slow(uint32_t x, uint32_t xprev, int valid, uint32_t dense_base) {
+template <uint32_t DB>
+__device__ __noinline__ void dense_word0_slow(uint32_t x, uint32_t xprev, int valid) {
     uint32_t p = (xprev >> 24) & 31u;
     for (int j = 0; j < valid && j < 4; j++) {
         const uint32_t b = (x >> (8 * j)) & 31u;
-        smem_inc(dense_base + 32768u + ((p << 7) | ((b ^ p) << 2)));
+        smem_inc(DB + COARSE_OFF + ((p << 8) | ((b ^ p) << 2)));
         p = b;
+    }
+}
+// the last, partial pair of a row (fewer than eight valid bytes): everything window by window
+template <uint32_t DB>
+__device__ __noinline__ void dense_pair_tail(uint32_t x0, uint32_t x1, uint32_t xprev, uint32_t t10, uint32_t t11, uint32_t t20,
+                                             uint32_t t21, uint32_t t30, uint32_t t31, uint32_t t40, uint32_t t41, uint32_t tp1,
+                                             uint32_t tp2, uint32_t tp3, uint32_t tp4, int valid0, uint32_t s_out_addr) {
+    dense_word0_slow<DB>(x0, xprev, valid0);
+    dense_word_slow<DB>(1u, t10, tp1, valid0, s_out_addr);
+    dense_word_slow<DB>(2u, t20, tp2, valid0, s_out_addr);
+    dense_word_slow<DB>(3u, t30, tp3, valid0, s_out_addr);
+    dense_word_slow<DB>(4u, t40, tp4, valid0, s_out_addr);
+    if (valid0 > 4) {
+        dense_word0_slow<DB>(x1, x0, valid0 - 4);
+        dense_word_slow<DB>(1u, t11, t10, valid0 - 4, s_out_addr);
+        dense_word_slow<DB>(2u, t21, t20, valid0 - 4, s_out_addr);
+        dense_word_slow<DB>(3u, t31, t30, valid0 - 4, s_out_addr);
+        dense_word_slow<DB>(4u, t41, t40, valid0 - 4, s_out_addr);
     }
 }
 
@@ -697,18 +734,13 @@ __device__ __noinline__ void bigram_flagged(const uint8_t *cur, const uint8_t *u
     }
 }
 
-template <int D, int NT>
+template <int D, int NT, uint32_t DB>
 __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
                                                      const Smem &sm, uint32_t h0_slots, const Prefetch &pf) {
+    static_assert(NT % 128 == 0, "the sweep gives every trial NT / 128 whole warps");
     const uint32_t nwords = (len + 3) >> 2, npairs = (nwords + 1) >> 1;
-    const uint32_t lane = threadIdx.x & 31u, rep = (lane >> 2) & 1u;
-    const uint32_t dense_base = smem_u32(sm.small);
-    const uint32_t c1 = rep * 0x10101010u, c2 = rep * 0x80808080u;
-    // Window rotation: byte j of a rotated word is byte (j + lane) & 3 of the word, so that the 32 lanes of one atomic
-    // mix the four channel pairs of RGBA instead of all hitting the same (few-valued) pair.  rt rotates a word; rp builds
-    // the rotated "bytes in front" word from (word, previous word): byte m of it is m ? word.byte[m-1] : previous.byte[3].
-    const uint32_t r0 = lane & 3u;
-    const uint32_t rt = (0x32103210u >> (4 * r0)) & 0xFFFFu, rp = (0x21072107u >> (4 * r0)) & 0xFFFFu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t s_out_addr = smem_u32(sm.s_out_());
     uint32_t nz = 0; // OR of this thread's row bytes (all-zero rows short-circuit to None, png/mod.rs:398-404)
     // thread t owns the row words 2t and 2t+1 (one 8-byte load per row and neighbour)
     for (uint32_t pr = threadIdx.x; pr < ((npairs + 31u) & ~31u); pr += NT) {
@@ -760,54 +792,56 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
         }
         if (pr < npairs) {
             const int valid0 = (int)len - 4 * k;
-            nz |= valid0 >= 8 ? (x[0] | x[1]) : ((x[0] & tail_mask(valid0)) | (x[1] & tail_mask(valid0 - 4)));
+            if (valid0 >= 8) { // both words complete (every pair of a row whose length is a multiple of 8)
+                nz |= x[0] | x[1];
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const int valid = valid0 - 4 * i;
-                if (valid <= 0) break;
-                const uint32_t xp = i ? x[0] : xprev;
-                if (valid >= 4) dense_word0(prmt(x[i], 0u, rt), prmt(x[i], xp, rp), dense_base);
-                else dense_word0_slow(x[i], xp, valid, dense_base);
+                for (int i = 0; i < 2; i++) {
+                    // "bytes in front" word: byte m is m ? word.byte[m-1] : previous word.byte[3]
+                    dense_word0<DB>(x[i], prmt(x[i], i ? x[0] : xprev, 0x2107u));
 #pragma unroll
-                for (int f = 0; f < 4; f++) {
-                    const uint32_t tp = i ? t[f][0] : tprev[f];
-                    const uint32_t tr = prmt(t[f][i], 0u, rt), tpr = prmt(t[f][i], tp, rp);
-                    if (valid >= 4 && ((tr | tpr) & 0xE0E0E0E0u) == 0) { // the common case: all four windows in range
-                        if (f == 0) dense_word<1>(tr, tpr, dense_base, c1, c2);
-                        if (f == 1) dense_word<2>(tr, tpr, dense_base, c1, c2);
-                        if (f == 2) dense_word<3>(tr, tpr, dense_base, c1, c2);
-                        if (f == 3) dense_word<4>(tr, tpr, dense_base, c1, c2);
-                    } else {
-                        dense_word_slow((uint32_t)f + 1u, t[f][i], tp, valid, dense_base, rep, sm.ohash, sm.s_out_());
+                    for (int f = 0; f < 4; f++) {
+                        const uint32_t tp = i ? t[f][0] : tprev[f];
+                        const uint32_t tpw = prmt(t[f][i], tp, 0x2107u);
+                        if (((t[f][i] | tpw) & 0xE0E0E0E0u) == 0) { // the common case: all four windows in range
+                            if (f == 0) dense_word<1, DB>(t[f][i], tpw);
+                            if (f == 1) dense_word<2, DB>(t[f][i], tpw);
+                            if (f == 2) dense_word<3, DB>(t[f][i], tpw);
+                            if (f == 3) dense_word<4, DB>(t[f][i], tpw);
+                        } else {
+                            dense_word_slow<DB>((uint32_t)f + 1u, t[f][i], tp, 4, s_out_addr);
+                        }
                     }
                 }
+            } else {
+                nz |= (x[0] & tail_mask(valid0)) | (x[1] & tail_mask(valid0 - 4));
+                dense_pair_tail<DB>(x[0], x[1], xprev, t[0][0], t[0][1], t[1][0], t[1][1], t[2][0], t[2][1], t[3][0], t[3][1],
+                                    tprev[0], tprev[1], tprev[2], tprev[3], valid0, s_out_addr);
             }
         }
     }
     __syncthreads();
     // every warp is past the previous row's write pass: with a 3-slot ring the oldest slot may be refilled from here on
     issue_prefetch<NT>(pf);
-    // sweep the dense tables (sum of the two replicas), four keys at a time, and the outlier hashes
+    // sweep (and clear) the dense tables, four keys at a time, and the outlier hashes.  Trial f belongs to NT / 128 whole
+    // warps, so its scores are summed in registers over the loop and added to the row's score set once per warp.
     {
+        constexpr uint32_t WPT = NT / 128; // warps per trial
         uint4 *dn = reinterpret_cast<uint4 *>(sm.small);
-        // trials 1..4: q = trial-1 : 2 | first : 5 | group of four seconds : 3
-        for (uint32_t q = threadIdx.x; q < 1024u; q += NT) {
-            const uint32_t f = 1u + (q >> 8), first = (q >> 3) & 31u, g = q & 7u;
-            uint4 *c0 = dn + first * 64u + (f - 1u) * 16u + g, *c1 = c0 - g + 8u + (g ^ 4u);
-            const uint4 a = *c0, b = *c1;
-            *c0 = make_uint4(0, 0, 0, 0);
-            *c1 = make_uint4(0, 0, 0, 0);
-            const uint32_t n0 = a.x + b.x, n1 = a.y + b.y, n2 = a.z + b.z, n3 = a.w + b.w;
-            uint32_t d = (n0 != 0) + (n1 != 0) + (n2 != 0) + (n3 != 0);
-            uint32_t e = ilog2i_z(n0) + ilog2i_z(n1) + ilog2i_z(n2) + ilog2i_z(n3);
-            // the trial's outlier hash table (HSLOTS / 4 cells, one per thread of the trial's first 128): counted unless
-            // the trial is flagged (then only cleared)
-            const uint32_t w = q & 255u;
-            if (w < HSLOTS / 4) {
-                uint4 *cell = reinterpret_cast<uint4 *>(sm.ohash + (f - 1) * HSLOTS) + w;
-                const uint4 v = *cell;
+        const uint32_t warp = threadIdx.x >> 5, f = 1u + warp / WPT;
+        uint32_t d = 0, e = 0;
+        // c = first : 5 | group of four seconds : 3
+        for (uint32_t c = (warp % WPT) * 32u + lane; c < 256u; c += WPT * 32u) {
+            uint4 *cell = dn + (c >> 3) * 32u + (f - 1u) * 8u + (c & 7u);
+            const uint4 a = *cell;
+            *cell = make_uint4(0, 0, 0, 0);
+            d += (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0);
+            e += ilog2i_z(a.x) + ilog2i_z(a.y) + ilog2i_z(a.z) + ilog2i_z(a.w);
+            // the trial's outlier hash table (HSLOTS / 4 cells): counted unless the trial is flagged (then only cleared)
+            if (c < HSLOTS / 4) {
+                uint4 *oc = reinterpret_cast<uint4 *>(sm.ohash + (f - 1) * HSLOTS) + c;
+                const uint4 v = *oc;
                 if (v.x | v.y | v.z | v.w) {
-                    *cell = make_uint4(0, 0, 0, 0);
+                    *oc = make_uint4(0, 0, 0, 0);
                     if (sm.s_out_()[f] == 0) {
                         if (v.x) { d += 1; e += ilog2i(v.x & 0xFFFFu); }
                         if (v.y) { d += 1; e += ilog2i(v.y & 0xFFFFu); }
@@ -816,29 +850,31 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
                     }
                 }
             }
-            // all 32 lanes of a warp sweep the same trial (256 cells per trial)
-            d = warp_sum(d);
-            e = warp_sum(e);
-            if (lane == 0 && d) {
-                atomicAdd(&sm.s_bgc_()[f], d);
-                atomicAdd(&sm.s_bge_()[f], e);
-            }
         }
-        // trial 0 (coarse keys): 1024 counters, four per step
+        d = warp_sum(d);
+        e = warp_sum(e);
+        if (lane == 0 && d) {
+            atomicAdd(&sm.s_bgc_()[f], d);
+            atomicAdd(&sm.s_bge_()[f], e);
+        }
+        // trial 0 (coarse keys): 1024 counters in 32 lines of 128 bytes (every other line of the 8 KB at COARSE_OFF)
         {
-            uint4 *d4 = reinterpret_cast<uint4 *>(sm.small) + 2048u;
-            uint32_t d = 0, e = 0;
+            uint4 *d4 = dn + COARSE_OFF / 16u;
+            uint32_t d0 = 0, e0 = 0;
             for (uint32_t q = threadIdx.x; q < 256u; q += NT) {
-                const uint4 a = d4[q];
-                d4[q] = make_uint4(0, 0, 0, 0);
-                d += (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0);
-                e += ilog2i_z(a.x) + ilog2i_z(a.y) + ilog2i_z(a.z) + ilog2i_z(a.w);
+                uint4 *cell = d4 + (q >> 3) * 16u + (q & 7u);
+                const uint4 a = *cell;
+                *cell = make_uint4(0, 0, 0, 0);
+                d0 += (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0);
+                e0 += ilog2i_z(a.x) + ilog2i_z(a.y) + ilog2i_z(a.z) + ilog2i_z(a.w);
             }
-            d = warp_sum(d);
-            e = warp_sum(e);
-            if (lane == 0 && d) {
-                atomicAdd(&sm.s_bgc_()[0], d);
-                atomicAdd(&sm.s_bge_()[0], e);
+            if (threadIdx.x < 256u) { // whole warps
+                d0 = warp_sum(d0);
+                e0 = warp_sum(e0);
+                if (lane == 0 && d0) {
+                    atomicAdd(&sm.s_bgc_()[0], d0);
+                    atomicAdd(&sm.s_bge_()[0], e0);
+                }
             }
         }
     }
@@ -957,6 +993,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (
     const int tid = threadIdx.x;
     const int bpp = (int)P.g.bpp;
     const uint32_t shift = P.shift;
+    if (smem_u32(smem_raw) != SMEM_WIN) __trap(); // the table atomics carry their shared-window address as an immediate
 
     if (tid == 0) {
         for (uint32_t i = 0; i < NS; i++) mbar_init(&sm.bar[i], 1);
@@ -1077,7 +1114,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (
                 if (SC & SC_BIGRAM) {
                     const uint32_t wpt = (((len + 3) >> 2) + NT - 1) / NT; // row words per thread
                     if ((SC & SC_HALF) || P.small_tab) {
-                        nz |= bigram_row_small<D, NT>(cur, up, len, shift, bpp, sr, P.h0_slots, pf);
+                        nz |= bigram_row_small<D, NT, SMEM_WIN + SMEM_HDR + ((SC & SC_ENTROPY) ? 5u * HIST_REP * 256u * 4u : 0u)>(cur, up, len, shift, bpp, sr, P.h0_slots, pf);
                         small_flow = true;
                     }
                     else if (wpt <= 1) bigram_row<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
@@ -1202,7 +1239,35 @@ KernelFn pick_kernel(int d, int sc) { return d == 0 ? pick_sc<0>(sc) : d == 1 ? 
 std::mutex g_occ_mu;
 std::map<std::pair<const void *, uint32_t>, int> g_occ; // (kernel, smem) -> resident CTAs per SM
 
+__global__ void k_probe_smem_window(uint32_t *out) {
+    extern __shared__ __align__(128) uint8_t probe_raw[];
+    *out = smem_u32(probe_raw);
+}
+
 } // namespace
+
+cudaError_t fast_tier_init(int device, uint32_t *smem_window) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
+    const int scs[6] = {0, SC_MINSUM, SC_ENTROPY, SC_BIGRAM, SC_BIGRAM | SC_HALF, SC_MINSUM | SC_ENTROPY | SC_BIGRAM};
+    for (int d = 0; d < 3; d++)
+        for (int i = 0; i < 6; i++) {
+            e = cudaFuncSetAttribute((const void *)pick_kernel(d, scs[i]), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)SMEM_LIMIT);
+            if (e != cudaSuccess) return e;
+        }
+    uint32_t *d_w = nullptr, w = 0;
+    e = cudaMalloc((void **)&d_w, sizeof w);
+    if (e != cudaSuccess) return e;
+    k_probe_smem_window<<<1, 32, 1024>>>(d_w);
+    e = cudaMemcpy(&w, d_w, sizeof w, cudaMemcpyDeviceToHost);
+    cudaFree(d_w);
+    if (e != cudaSuccess) return e;
+    *smem_window = w;
+    return cudaSuccess;
+}
+// the bigram and Entropy scorers address their tables as [register + immediate] from SMEM_WIN
+bool fast_tier_usable(uint32_t smem_window) { return smem_window == SMEM_WIN; }
 
 bool fast_supported(const Geom &g, const StrategySet &set) {
     if (g.alpha_bytes != 0 || g.total_rows == 0) return false;
@@ -1238,8 +1303,7 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
     P.nslot = (sc != 0 && P.rb <= 16448 && smem_bytes_for(sc, P.rb, P.h0_slots, 4) <= budget) ? 4 : 3;
     const uint32_t smem = smem_bytes_for(sc, P.rb, P.h0_slots, P.nslot);
     KernelFn fn = pick_kernel((int)(g.bpp / 4), sc);
-    cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    cudaError_t e; // (the dynamic shared-memory limit was raised once per device by fast_tier_init)
     int occ = 0;
     {
         std::lock_guard<std::mutex> lk(g_occ_mu);
