@@ -167,6 +167,50 @@ int oxi_interlace_image(const oxi_ihdr *, const uint8_t *data, size_t data_len, 
 /* deinterlace_image, src/interlace.rs:62-150: Adam7 layout -> progressive layout. out: ceil(width*bpp/8)*height */
 int oxi_deinterlace_image(const oxi_ihdr *, const uint8_t *data, size_t data_len, uint8_t *out, size_t *out_len);
 
+/* ---- device-resident images (oxi_image_upload / oxi_image_free; 8f row 3) -------------------------
+ * An oxi_image owns PngImage.data in HBM with its IhdrData and palette / tRNS.  Every call below runs on the image's
+ * stream (cudaStream_t as void*, may be NULL) and derived images inherit it, so perform_reductions
+ * (src/reduction/mod.rs:14-179) and the evaluator (src/evaluate.rs:126-201) chain on one stream: pixels cross PCIe
+ * once in (upload) and only the filtered streams come back.  A reduction returns OXI_NONE exactly where the reference
+ * function returns None (*out is then NULL); the scan results that decide this (a few bytes) are read back
+ * synchronously, the images themselves never leave the device.  Free every image with oxi_image_free. */
+typedef struct oxi_image oxi_image;
+int oxi_image_upload(int device, void *stream, const oxi_ihdr *, const oxi_color_aux * /* may be NULL */, const uint8_t *data,
+                     size_t len, oxi_image **out);
+/* the same from bytes already on the device (copied, stream ordered) */
+int oxi_image_wrap_device(int device, void *stream, const oxi_ihdr *, const oxi_color_aux *, const uint8_t *d_data, size_t len,
+                          oxi_image **out);
+/* PngImage::new -> unfilter_image (png/mod.rs:335-351): upload the inflated IDAT stream and unfilter it on the device */
+int oxi_image_from_filtered(int device, void *stream, const oxi_ihdr *, const oxi_color_aux *, const uint8_t *filtered,
+                            size_t len, oxi_image **out);
+void oxi_image_free(oxi_image *);
+int oxi_image_info(const oxi_image *, oxi_ihdr *, oxi_color_aux *, size_t *len);
+const uint8_t *oxi_image_device_ptr(const oxi_image *);
+int oxi_image_download(const oxi_image *, uint8_t *out, size_t cap, size_t *len); /* synchronises */
+int oxi_image_sync(const oxi_image *);
+/* reductions, handle -> handle: same semantics as the host-buffer entry points above */
+int oxi_cleaned_alpha_channel_device(const oxi_image *, oxi_image **out);
+int oxi_reduced_alpha_channel_device(const oxi_image *, int optimize_alpha, oxi_image **out);
+int oxi_reduced_bit_depth_16_to_8_device(const oxi_image *, int force_scale, oxi_image **out);
+int oxi_reduced_bit_depth_8_or_less_device(const oxi_image *, oxi_image **out);
+int oxi_expanded_bit_depth_to_8_device(const oxi_image *, oxi_image **out);
+int oxi_reduced_to_indexed_device(const oxi_image *, int allow_grayscale, oxi_image **out);
+int oxi_reduced_rgb_to_grayscale_device(const oxi_image *, oxi_image **out);
+int oxi_reduced_palette_device(const oxi_image *, int optimize_alpha, oxi_image **out);
+int oxi_sorted_palette_device(const oxi_image *, oxi_image **out);
+int oxi_apply_palette_reorder_device(const oxi_image *, const uint32_t *remapping, oxi_image **out);
+int oxi_cooccurrence_build_device(const oxi_image *, uint32_t num_colors, uint32_t *matrix /* host */);
+int oxi_used_histogram256_device(const oxi_image *, uint64_t hist[256] /* host */);
+int oxi_interlace_image_device(const oxi_image *, oxi_image **out);
+int oxi_deinterlace_image_device(const oxi_image *, oxi_image **out);
+/* evaluator candidate (evaluate.rs:141-153): k strategies on the resident image; only the filtered streams and the
+ * filters used come back to host memory (outs[j]: len + rows bytes, filters_used[j]: rows bytes) */
+int oxi_image_filter(const oxi_image *, const oxi_strategy *strategies, size_t k, int optimize_alpha, uint8_t *const *outs,
+                     uint8_t *const *filters_used, unsigned flags);
+/* the same into device buffers, asynchronous */
+int oxi_image_filter_device(const oxi_image *, const oxi_strategy *strategies, size_t k, int optimize_alpha,
+                            uint8_t *const *d_outs, uint8_t *const *d_filters_used, unsigned flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "liboxipng_b200.so")
-SOURCES = ["capi.cu", "filter_generic.cu", "filter_fast.cu", "reduce.cu"]
+SOURCES = ["capi.cu", "filter_generic.cu", "filter_fast.cu", "reduce.cu", "image.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler",
               "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
 

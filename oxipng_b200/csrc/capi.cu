@@ -134,6 +134,13 @@ DeviceCtx *get_ctx(int device, int *err) {
     DeviceCtx *c = new DeviceCtx;
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
+    {   // keep the stream-ordered pool's memory across synchronisations (oxi_image_* allocate from it per reduction)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     e = fast_tier_init(device, &c->smem_window);
     if (e != cudaSuccess) { delete c; *err = fail_cuda(e, "fast_tier_init"); return nullptr; }
     g_ctx[device] = c;
@@ -332,6 +339,34 @@ int filter_host_chunk(DeviceCtx *c, Slot *slot, const Geom &g, const uint8_t *da
     return OXI_OK;
 }
 
+// Filter search on device-resident images (oxi_filter_batch_device, oxi_image_filter*): enqueues on `stream`, returns
+// without synchronising.
+int filter_resident(int device, cudaStream_t stream, const oxi_ihdr *h, const uint8_t *d_data, size_t data_len, size_t n_images,
+                    const oxi_strategy *strategies, size_t k, int optimize_alpha, uint8_t *const *d_outs,
+                    uint8_t *const *d_filters_used, unsigned flags) {
+    Geom g;
+    if (!build_geom(h, data_len, optimize_alpha, &g)) return fail(OXI_E_ARG, "invalid IHDR");
+    if (g.data_len != data_len) return fail(OXI_E_ARG, "data_len is not a whole number of scanlines for this IHDR");
+    if (!d_data || !d_outs || !d_filters_used || !strategies) return fail(OXI_E_ARG, "null pointer");
+    int err = 0;
+    DeviceCtx *c = get_ctx(device, &err);
+    if (!c) return err;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
+    // scratch (Predefined lists, generic-tier rows) comes from a pooled slot; the work runs on the caller's stream and
+    // the slot goes back with an event, so nothing is shared between concurrent callers and nothing synchronises
+    Slot *slot = acquire_slot(c);
+    if (!slot) return fail(OXI_E_CUDA, "cannot create stream");
+    StrategySet set;
+    int rc = OXI_OK;
+    e = slot_begin(slot, stream);
+    if (e != cudaSuccess) rc = fail_cuda(e, "cudaStreamWaitEvent");
+    if (rc == OXI_OK) rc = make_set(slot, stream, strategies, k, d_outs, d_filters_used, &set);
+    if (rc == OXI_OK) rc = run_filters(c, slot, stream, g, d_data, n_images, set, flags);
+    release_slot_async(c, slot, stream);
+    return rc;
+}
+
 } // namespace oxi
 
 using namespace oxi;
@@ -418,28 +453,8 @@ const char *oxi_filter_tier(const oxi_ihdr *h, size_t data_len, const oxi_strate
 int oxi_filter_batch_device(int device, void *stream, const oxi_ihdr *h, const uint8_t *d_data, size_t data_len,
                             size_t n_images, const oxi_strategy *strategies, size_t k, int optimize_alpha,
                             uint8_t *const *d_outs, uint8_t *const *d_filters_used, unsigned flags) {
-    Geom g;
-    if (!build_geom(h, data_len, optimize_alpha, &g)) return fail(OXI_E_ARG, "invalid IHDR");
-    if (g.data_len != data_len) return fail(OXI_E_ARG, "data_len is not a whole number of scanlines for this IHDR");
-    if (!d_data || !d_outs || !d_filters_used || !strategies) return fail(OXI_E_ARG, "null pointer");
-    int err = 0;
-    DeviceCtx *c = get_ctx(device, &err);
-    if (!c) return err;
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
-    // scratch (Predefined lists, generic-tier rows) comes from a pooled slot; the work runs on the caller's stream and
-    // the slot goes back with an event, so nothing is shared between concurrent callers and nothing synchronises
-    Slot *slot = acquire_slot(c);
-    if (!slot) return fail(OXI_E_CUDA, "cannot create stream");
-    const cudaStream_t st = (cudaStream_t)stream;
-    StrategySet set;
-    int rc = OXI_OK;
-    e = slot_begin(slot, st);
-    if (e != cudaSuccess) rc = fail_cuda(e, "cudaStreamWaitEvent");
-    if (rc == OXI_OK) rc = make_set(slot, st, strategies, k, d_outs, d_filters_used, &set);
-    if (rc == OXI_OK) rc = run_filters(c, slot, st, g, d_data, n_images, set, flags);
-    release_slot_async(c, slot, st);
-    return rc;
+    return filter_resident(device, (cudaStream_t)stream, h, d_data, data_len, n_images, strategies, k, optimize_alpha, d_outs,
+                           d_filters_used, flags);
 }
 
 int oxi_filter_batch(const oxi_ihdr *h, const uint8_t *data, size_t data_len, size_t n_images,

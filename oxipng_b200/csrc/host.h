@@ -57,6 +57,9 @@ struct DevIOScope {
 };
 
 DeviceCtx *get_ctx(int device, int *err);
+int filter_resident(int device, cudaStream_t stream, const oxi_ihdr *h, const uint8_t *d_data, size_t data_len, size_t n_images,
+                    const oxi_strategy *strategies, size_t k, int optimize_alpha, uint8_t *const *d_outs,
+                    uint8_t *const *d_filters_used, unsigned flags);
 DeviceCtx *current_ctx(int *err); // context of the calling thread's device (oxi_set_device), cudaSetDevice done
 Slot *acquire_slot(DeviceCtx *c);
 void release_slot(DeviceCtx *c, Slot *s);

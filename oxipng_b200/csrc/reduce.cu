@@ -720,43 +720,74 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
 struct Call {
     DeviceCtx *c = nullptr;
     Slot *s = nullptr;
+    cudaStream_t stream = nullptr; // the slot's own stream, or the caller's in device-resident mode
+    bool resident = false;         // device-resident mode (host.h DevIO): data / out are device pointers
     int err = 0;
     ScanState *st = nullptr; // device
     uint8_t *d_in = nullptr, *d_out = nullptr;
     uint8_t *extra = nullptr; // scratch after ScanState (tables, LUTs)
 
-    Call(const uint8_t *data, size_t len, size_t out_cap, size_t extra_bytes = 0) {
-        c = current_ctx(&err);
+    // `out` = the caller's output buffer (host, or device in device-resident mode; may be null when the call has no
+    // image output)
+    Call(const uint8_t *data, size_t len, uint8_t *out, size_t out_cap, size_t extra_bytes = 0) {
+        resident = t_devio != nullptr;
+        if (resident) {
+            c = get_ctx(t_devio->device, &err);
+            if (c && cudaSetDevice(c->device) != cudaSuccess) { err = fail(OXI_E_CUDA, "cudaSetDevice"); c = nullptr; }
+        } else {
+            c = current_ctx(&err);
+        }
         if (!c) return;
         s = acquire_slot(c);
         if (!s) { err = fail(OXI_E_CUDA, "cannot create stream"); return; }
-        cudaError_t e = grow(&s->d_in, &s->in_cap, len + 64);
-        if (e == cudaSuccess) e = grow(&s->d_out, &s->out_cap, out_cap + 64);
+        stream = resident ? t_devio->stream : s->stream;
+        cudaError_t e = slot_begin(s, stream);
+        if (e == cudaSuccess && !resident) {
+            e = grow(&s->d_in, &s->in_cap, len + 64);
+            if (e == cudaSuccess) e = grow(&s->d_out, &s->out_cap, out_cap + 64);
+        }
         if (e == cudaSuccess) e = grow(&s->scratch, &s->scratch_bytes, sizeof(ScanState) + extra_bytes + 256);
         if (e != cudaSuccess) { err = fail_cuda(e, "cudaMalloc"); return; }
-        d_in = s->d_in;
-        d_out = s->d_out;
+        d_in = resident ? const_cast<uint8_t *>(data) : s->d_in;
+        d_out = resident ? out : s->d_out;
         st = reinterpret_cast<ScanState *>(s->scratch);
         extra = s->scratch + ((sizeof(ScanState) + 255) & ~(size_t)255);
-        e = cudaMemsetAsync(st, 0, sizeof(ScanState), s->stream);
-        if (e == cudaSuccess && len) e = cudaMemcpyAsync(d_in, data, len, cudaMemcpyHostToDevice, s->stream);
+        e = cudaMemsetAsync(st, 0, sizeof(ScanState), stream);
+        if (e == cudaSuccess && len && !resident) e = cudaMemcpyAsync(d_in, data, len, cudaMemcpyHostToDevice, stream);
         if (e != cudaSuccess) err = fail_cuda(e, "upload");
     }
     ~Call() {
-        if (s) {
-            cudaStreamSynchronize(s->stream);
+        if (!s) return;
+        if (resident) {
+            release_slot_async(c, s, stream); // nothing synchronises: the scratch is reused in stream order
+        } else {
+            cudaStreamSynchronize(stream);
             release_slot(c, s);
         }
     }
     bool ok() const { return err == 0; }
     int state(ScanState *h) {
-        cudaError_t e = cudaMemcpyAsync(h, st, sizeof(ScanState), cudaMemcpyDeviceToHost, s->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        cudaError_t e = cudaMemcpyAsync(h, st, sizeof(ScanState), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         return e == cudaSuccess ? 0 : fail_cuda(e, "download scan state");
     }
+    // the image result: already in place in device-resident mode
     int download(uint8_t *out, size_t n) {
-        cudaError_t e = n ? cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, s->stream) : cudaSuccess;
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (resident) return 0;
+        cudaError_t e = n ? cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, stream) : cudaSuccess;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        return e == cudaSuccess ? 0 : fail_cuda(e, "download");
+    }
+    // result = the input bytes unchanged
+    int passthrough(uint8_t *out, const uint8_t *data, size_t n) {
+        if (!resident) { memcpy(out, data, n); return 0; }
+        cudaError_t e = cudaMemcpyAsync(out, data, n, cudaMemcpyDeviceToDevice, stream);
+        return e == cudaSuccess ? 0 : fail_cuda(e, "device copy");
+    }
+    // small results (histograms, matrices) always go to host memory
+    int to_host(void *dst, const void *d_src, size_t n) {
+        cudaError_t e = cudaMemcpyAsync(dst, d_src, n, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         return e == cudaSuccess ? 0 : fail_cuda(e, "download");
     }
     int check(const char *what) {
@@ -797,9 +828,9 @@ void copy_aux(oxi_color_aux *dst, const oxi_color_aux *src) {
 
 // LUT remap of a device-resident image already uploaded by `call`
 int run_lut(Call &call, size_t len, const uint8_t lut[256]) {
-    cudaError_t e = cudaMemcpyAsync(call.extra, lut, 256, cudaMemcpyHostToDevice, call.s->stream);
+    cudaError_t e = cudaMemcpyAsync(call.extra, lut, 256, cudaMemcpyHostToDevice, call.stream);
     if (e != cudaSuccess) return fail_cuda(e, "upload LUT");
-    k_lut<<<grid_for((len + 15) / 16, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, len, call.extra);
+    k_lut<<<grid_for((len + 15) / 16, call.c->num_sms), RT, 0, call.stream>>>(call.d_in, call.d_out, len, call.extra);
     return call.check("k_lut");
 }
 
@@ -820,10 +851,10 @@ int oxi_cleaned_alpha_channel(const oxi_ihdr *h, const uint8_t *data, size_t len
     if (!has_alpha(h->color_type)) return OXI_NONE; // alpha.rs:12-14
     const uint32_t bd = (uint32_t)byte_depth(h), bpp = (uint32_t)channels(h->color_type) * bd, cb = bpp - bd;
     const size_t used = len / bpp * bpp; // chunks_exact
-    Call call(data, len, len);
+    Call call(data, len, out, len);
     if (!call.ok()) return call.err;
     const uint64_t n16 = used / 16;
-    k_clean_alpha<<<grid_for(n16 ? n16 : 1, call.c->num_sms), RT, 0, call.s->stream>>>(
+    k_clean_alpha<<<grid_for(n16 ? n16 : 1, call.c->num_sms), RT, 0, call.stream>>>(
         reinterpret_cast<const uint4 *>(call.d_in), reinterpret_cast<uint4 *>(call.d_out), n16, call.d_in + n16 * 16,
         call.d_out + n16 * 16, (uint32_t)(used - n16 * 16), bpp, cb);
     if (int rc = call.check("k_clean_alpha")) return rc;
@@ -836,9 +867,9 @@ int oxi_reduced_alpha_channel(const oxi_ihdr *h, const uint8_t *data, size_t len
     if (!has_alpha(h->color_type)) return OXI_NONE;
     const uint32_t bd = (uint32_t)byte_depth(h), bpp = (uint32_t)channels(h->color_type) * bd, cb = bpp - bd;
     const uint64_t npix = len / bpp;
-    Call call(data, len, npix * cb);
+    Call call(data, len, out, npix * cb);
     if (!call.ok()) return call.err;
-    k_alpha_scan<<<grid_for(npix, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, npix, bpp, cb, optimize_alpha, call.st);
+    k_alpha_scan<<<grid_for(npix, call.c->num_sms), RT, 0, call.stream>>>(call.d_in, npix, bpp, cb, optimize_alpha, call.st);
     if (int rc = call.check("k_alpha_scan")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
@@ -855,7 +886,7 @@ int oxi_reduced_alpha_channel(const oxi_ihdr *h, const uint8_t *data, size_t len
             if (!used(v)) trns = v;
         if (trns < 0) return OXI_NONE;
     }
-    k_alpha_strip<<<grid_for(npix, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, npix, bpp, cb, trns);
+    k_alpha_strip<<<grid_for(npix, call.c->num_sms), RT, 0, call.stream>>>(call.d_in, call.d_out, npix, bpp, cb, trns);
     if (int rc = call.check("k_alpha_strip")) return rc;
     if (int rc = call.download(out, npix * cb)) return rc;
     if (out_len) *out_len = npix * cb;
@@ -876,9 +907,9 @@ int oxi_reduced_bit_depth_16_to_8(const oxi_ihdr *h, const uint8_t *data, size_t
     if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
     if (h->bit_depth != 16) return OXI_NONE;
     const uint64_t ns = len / 2;
-    Call call(data, len, ns);
+    Call call(data, len, out, ns);
     if (!call.ok()) return call.err;
-    k_16to8<<<grid_for((ns + 7) / 8, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, ns, force_scale ? 1 : 0,
+    k_16to8<<<grid_for((ns + 7) / 8, call.c->num_sms), RT, 0, call.stream>>>(call.d_in, call.d_out, ns, force_scale ? 1 : 0,
                                                                                  call.st);
     if (int rc = call.check("k_16to8")) return rc;
     if (!force_scale) {
@@ -898,7 +929,7 @@ int oxi_reduced_bit_depth_8_or_less(const oxi_ihdr *h, const oxi_color_aux *aux,
     if (h->bit_depth != 8 || channels(h->color_type) != 1) return OXI_NONE;
     Geom g;
     if (!build_geom(h, len, 0, &g)) return fail(OXI_E_ARG, "invalid IHDR");
-    Call call(data, len, len);
+    Call call(data, len, out, len);
     if (!call.ok()) return call.err;
     uint32_t bits;
     if (h->color_type == 3) { // bit_depth.rs:73-80
@@ -908,7 +939,7 @@ int oxi_reduced_bit_depth_8_or_less(const oxi_ihdr *h, const oxi_color_aux *aux,
         else if (n <= 16) bits = 4;
         else return OXI_NONE;
     } else {
-        k_min_bits<<<grid_for((len + 15) / 16, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, len, call.st);
+        k_min_bits<<<grid_for((len + 15) / 16, call.c->num_sms), RT, 0, call.stream>>>(call.d_in, len, call.st);
         if (int rc = call.check("k_min_bits")) return rc;
         ScanState st;
         if (int rc = call.state(&st)) return rc;
@@ -919,7 +950,7 @@ int oxi_reduced_bit_depth_8_or_less(const oxi_ihdr *h, const oxi_color_aux *aux,
     RowMap m;
     make_row_map(g, [per](const PassDesc &pd) { return (pd.len + per - 1) / per; }, &m);
     const uint64_t total = m.out_items[g.n_pass];
-    k_pack_bits<<<grid_for(total, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, m, bits);
+    k_pack_bits<<<grid_for(total, call.c->num_sms), RT, 0, call.stream>>>(call.d_in, call.d_out, m, bits);
     if (int rc = call.check("k_pack_bits")) return rc;
     if (int rc = call.download(out, total)) return rc;
     if (out_len) *out_len = total;
@@ -948,9 +979,9 @@ int oxi_expanded_bit_depth_to_8(const oxi_ihdr *h, const oxi_color_aux *aux, con
     RowMap m;
     make_row_map(g, [](const PassDesc &pd) { return pd.pixels; }, &m);
     const uint64_t total = m.out_items[g.n_pass];
-    Call call(data, len, total);
+    Call call(data, len, out, total);
     if (!call.ok()) return call.err;
-    k_expand_bits<<<grid_for(total, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, m, depth,
+    k_expand_bits<<<grid_for(total, call.c->num_sms), RT, 0, call.stream>>>(call.d_in, call.d_out, m, depth,
                                                                                h->color_type == 0);
     if (int rc = call.check("k_expand_bits")) return rc;
     if (int rc = call.download(out, total)) return rc;
@@ -973,9 +1004,9 @@ int oxi_reduced_rgb_to_grayscale(const oxi_ihdr *h, const oxi_color_aux *aux, co
     if (h->color_type != 2 && h->color_type != 6) return OXI_NONE;
     const uint32_t bd = (uint32_t)byte_depth(h), bpp = (uint32_t)channels(h->color_type) * bd, keep = bpp - 2 * bd;
     const uint64_t npix = len / bpp;
-    Call call(data, len, npix * keep);
+    Call call(data, len, out, npix * keep);
     if (!call.ok()) return call.err;
-    k_rgb_to_gray<<<grid_for(npix, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, npix, bpp, bd, call.st);
+    k_rgb_to_gray<<<grid_for(npix, call.c->num_sms), RT, 0, call.stream>>>(call.d_in, call.d_out, npix, bpp, bd, call.st);
     if (int rc = call.check("k_rgb_to_gray")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
@@ -1001,23 +1032,23 @@ int oxi_reduced_to_indexed(const oxi_ihdr *h, const oxi_color_aux *aux, const ui
     if (!allow_grayscale && gray) return OXI_NONE;
     const uint32_t ch = (uint32_t)channels(h->color_type);
     const uint64_t npix = len / ch;
-    Call call(data, len, npix, sizeof(ColorTable));
+    Call call(data, len, out, npix, sizeof(ColorTable));
     if (!call.ok()) return call.err;
     ColorTable *tab = reinterpret_cast<ColorTable *>(call.extra);
-    cudaError_t e = cudaMemsetAsync(tab->key, 0, sizeof tab->key, call.s->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(tab->first, 0xFF, sizeof tab->first, call.s->stream);
+    cudaError_t e = cudaMemsetAsync(tab->key, 0, sizeof tab->key, call.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(tab->first, 0xFF, sizeof tab->first, call.stream);
     if (e != cudaSuccess) return fail_cuda(e, "memset colour table");
     if (npix) {
-        k_collect_colors<<<grid_for(npix, call.c->num_sms, 4), RT, 0, call.s->stream>>>(call.d_in, npix, ch, tab, call.st);
+        k_collect_colors<<<grid_for(npix, call.c->num_sms, 4), RT, 0, call.stream>>>(call.d_in, npix, ch, tab, call.st);
         if (int rc = call.check("k_collect_colors")) return rc;
     }
     ScanState st;
     if (int rc = call.state(&st)) return rc;
     if (st.overflow || st.n_distinct > 256) return OXI_NONE; // 257th distinct colour (color.rs:29-31)
     std::vector<unsigned long long> keys(GSLOTS), first(GSLOTS);
-    e = cudaMemcpyAsync(keys.data(), tab->key, sizeof tab->key, cudaMemcpyDeviceToHost, call.s->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(first.data(), tab->first, sizeof tab->first, cudaMemcpyDeviceToHost, call.s->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(call.s->stream);
+    e = cudaMemcpyAsync(keys.data(), tab->key, sizeof tab->key, cudaMemcpyDeviceToHost, call.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(first.data(), tab->first, sizeof tab->first, cudaMemcpyDeviceToHost, call.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(call.stream);
     if (e != cudaSuccess) return fail_cuda(e, "download colour table");
     std::vector<uint32_t> slots;
     for (uint32_t s = 0; s < GSLOTS; s++)
@@ -1025,12 +1056,12 @@ int oxi_reduced_to_indexed(const oxi_ihdr *h, const oxi_color_aux *aux, const ui
     std::sort(slots.begin(), slots.end(), [&](uint32_t a, uint32_t b) { return first[a] < first[b]; }); // insertion order
     std::vector<uint32_t> index(GSLOTS, 0);
     for (size_t i = 0; i < slots.size(); i++) index[slots[i]] = (uint32_t)i;
-    e = cudaMemcpyAsync(tab->index, index.data(), sizeof tab->index, cudaMemcpyHostToDevice, call.s->stream);
+    e = cudaMemcpyAsync(tab->index, index.data(), sizeof tab->index, cudaMemcpyHostToDevice, call.stream);
     if (e != cudaSuccess) return fail_cuda(e, "upload palette indices");
     if (npix) {
         const size_t smem = GSLOTS * 8 + GSLOTS;
         cudaFuncSetAttribute((const void *)k_index_colors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_index_colors<<<grid_for(npix, call.c->num_sms, 4), RT, smem, call.s->stream>>>(call.d_in, call.d_out, npix, ch, tab);
+        k_index_colors<<<grid_for(npix, call.c->num_sms, 4), RT, smem, call.stream>>>(call.d_in, call.d_out, npix, ch, tab);
         if (int rc = call.check("k_index_colors")) return rc;
     }
     if (int rc = call.download(out, npix)) return rc;
@@ -1065,9 +1096,9 @@ int oxi_reduced_to_indexed(const oxi_ihdr *h, const oxi_color_aux *aux, const ui
 
 int oxi_used_histogram256(const uint8_t *data, size_t len, uint64_t hist[256]) {
     if (!data || !hist) return fail(OXI_E_ARG, "bad arguments");
-    Call call(data, len, 0);
+    Call call(data, len, nullptr, 0);
     if (!call.ok()) return call.err;
-    k_hist256<<<grid_for((len + 15) / 16, call.c->num_sms, 2), RT, 0, call.s->stream>>>(call.d_in, len, call.st);
+    k_hist256<<<grid_for((len + 15) / 16, call.c->num_sms, 2), RT, 0, call.stream>>>(call.d_in, len, call.st);
     if (int rc = call.check("k_hist256")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
@@ -1077,7 +1108,7 @@ int oxi_used_histogram256(const uint8_t *data, size_t len, uint64_t hist[256]) {
 
 int oxi_lut_remap(const uint8_t *data, size_t len, const uint8_t lut[256], uint8_t *out) {
     if (!data || !out || !lut) return fail(OXI_E_ARG, "bad arguments");
-    Call call(data, len, len, 256);
+    Call call(data, len, out, len, 256);
     if (!call.ok()) return call.err;
     if (int rc = run_lut(call, len, lut)) return rc;
     return call.download(out, len);
@@ -1086,9 +1117,9 @@ int oxi_lut_remap(const uint8_t *data, size_t len, const uint8_t lut[256], uint8
 int oxi_edge_color_counts(const oxi_ihdr *h, const uint8_t *data, size_t len, uint32_t counts[256]) {
     Geom g;
     if (!data || !counts || !build_geom(h, len, 0, &g)) return fail(OXI_E_ARG, "bad arguments");
-    Call call(data, len, 0);
+    Call call(data, len, nullptr, 0);
     if (!call.ok()) return call.err;
-    k_edge_counts<<<grid_for(g.total_rows, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, g, call.st);
+    k_edge_counts<<<grid_for(g.total_rows, call.c->num_sms), RT, 0, call.stream>>>(call.d_in, g, call.st);
     if (int rc = call.check("k_edge_counts")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
@@ -1100,9 +1131,9 @@ int oxi_reduced_palette(const oxi_ihdr *h, const oxi_color_aux *aux, const uint8
                         uint8_t *out, oxi_color_aux *oaux) {
     if (!valid_ihdr(h) || !data || !out) return fail(OXI_E_ARG, "bad arguments");
     if (h->bit_depth != 8 || h->color_type != 3 || !aux) return OXI_NONE; // palette.rs:13-18
-    Call call(data, len, len, 256);
+    Call call(data, len, out, len, 256);
     if (!call.ok()) return call.err;
-    k_hist256<<<grid_for((len + 15) / 16, call.c->num_sms, 2), RT, 0, call.s->stream>>>(call.d_in, len, call.st);
+    k_hist256<<<grid_for((len + 15) / 16, call.c->num_sms, 2), RT, 0, call.stream>>>(call.d_in, len, call.st);
     if (int rc = call.check("k_hist256")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
@@ -1126,7 +1157,7 @@ int oxi_reduced_palette(const oxi_ihdr *h, const oxi_color_aux *aux, const uint8
         if (int rc = run_lut(call, len, byte_map)) return rc;
         if (int rc = call.download(out, len)) return rc;
     } else if (nc != aux->n_palette) { // palette.rs:44-47: data unchanged, palette resized
-        memcpy(out, data, len);
+        if (int rc = call.passthrough(out, data, len)) return rc;
     } else {
         return OXI_NONE;
     }
@@ -1145,9 +1176,9 @@ int oxi_sorted_palette(const oxi_ihdr *h, const oxi_color_aux *aux, const uint8_
     Geom g;
     if (!build_geom(h, len, 0, &g)) return fail(OXI_E_ARG, "invalid IHDR");
     const uint32_t n = aux->n_palette > 256 ? 256 : aux->n_palette;
-    Call call(data, len, len, 256);
+    Call call(data, len, out, len, 256);
     if (!call.ok()) return call.err;
-    k_edge_counts<<<grid_for(g.total_rows, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, g, call.st);
+    k_edge_counts<<<grid_for(g.total_rows, call.c->num_sms), RT, 0, call.stream>>>(call.d_in, g, call.st);
     if (int rc = call.check("k_edge_counts")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
@@ -1199,7 +1230,7 @@ int oxi_apply_palette_reorder(const oxi_ihdr *h, const oxi_color_aux *aux, const
         memcpy(na.palette[i], aux->palette[remapping[i]], 4);
         byte_map[remapping[i]] = (uint8_t)i;
     }
-    Call call(data, len, len, 256);
+    Call call(data, len, out, len, 256);
     if (!call.ok()) return call.err;
     if (int rc = run_lut(call, len, byte_map)) return rc;
     if (int rc = call.download(out, len)) return rc;
@@ -1236,9 +1267,9 @@ int oxi_interlace_image(const oxi_ihdr *h, const uint8_t *data, size_t len, uint
     Adam7 a;
     make_adam7(h, &a);
     if (len < (size_t)a.full_stride * h->height) return fail(OXI_E_ARG, "data shorter than the progressive image");
-    Call call(data, len, a.base[7]);
+    Call call(data, len, out, a.base[7]);
     if (!call.ok()) return call.err;
-    k_interlace<<<grid_for(a.base[7], call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, a);
+    k_interlace<<<grid_for(a.base[7], call.c->num_sms), RT, 0, call.stream>>>(call.d_in, call.d_out, a);
     if (int rc = call.check("k_interlace")) return rc;
     if (int rc = call.download(out, a.base[7])) return rc;
     if (out_len) *out_len = a.base[7];
@@ -1251,9 +1282,9 @@ int oxi_deinterlace_image(const oxi_ihdr *h, const uint8_t *data, size_t len, ui
     make_adam7(h, &a);
     if (len < a.base[7]) return fail(OXI_E_ARG, "data shorter than the interlaced image");
     const size_t total = (size_t)a.full_stride * h->height;
-    Call call(data, len, total);
+    Call call(data, len, out, total);
     if (!call.ok()) return call.err;
-    k_deinterlace<<<grid_for(total, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, call.d_out, a);
+    k_deinterlace<<<grid_for(total, call.c->num_sms), RT, 0, call.stream>>>(call.d_in, call.d_out, a);
     if (int rc = call.check("k_deinterlace")) return rc;
     if (int rc = call.download(out, total)) return rc;
     if (out_len) *out_len = total;
@@ -1276,10 +1307,10 @@ int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, u
     build_geom(h, lo, 0, &g);
     if (g.total_rows == 0) { if (out_len) *out_len = 0; return OXI_OK; }
     const size_t prog_bytes = (size_t)g.n_pass * UF_CTAS * UF_WARPS * sizeof(unsigned long long);
-    Call call(filtered, len, g.data_len, prog_bytes);
+    Call call(filtered, len, out, g.data_len, prog_bytes);
     if (!call.ok()) return call.err;
     unsigned long long *prog = reinterpret_cast<unsigned long long *>(call.extra);
-    if (cudaMemsetAsync(prog, 0, prog_bytes, call.s->stream) != cudaSuccess) return fail(OXI_E_CUDA, "memset(progress)");
+    if (cudaMemsetAsync(prog, 0, prog_bytes, call.stream) != cudaSuccess) return fail(OXI_E_CUDA, "memset(progress)");
     {
         // the tiles of a pass wait on each other across CTAs: a cooperative launch guarantees that all of them are
         // resident together (<= 7 x 32 CTAs of 128 threads) even when other streams keep the device busy
@@ -1290,7 +1321,7 @@ int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, u
         void *args[] = {&g, &din, &dout, &one, &stride, &sst, &prog};
         const void *fn = g.bpp == 4 ? (const void *)k_unfilter<4> : (const void *)k_unfilter<0>;
         cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(g.n_pass * UF_CTAS), dim3(UF_WARPS * 32),
-                                                    args, 0, call.s->stream);
+                                                    args, 0, call.stream);
         if (e != cudaSuccess) return fail_cuda(e, "cudaLaunchCooperativeKernel(k_unfilter)");
     }
     if (int rc = call.check("k_unfilter")) return rc;
@@ -1307,22 +1338,20 @@ int oxi_cooccurrence_build(const oxi_ihdr *h, uint32_t n, const uint8_t *data, s
     if (!data || !matrix || n == 0 || n > 256 || !build_geom(h, len, 0, &g)) return fail(OXI_E_ARG, "bad arguments");
     if (h->bit_depth != 8) return fail(OXI_E_ARG, "co-occurrence needs 8-bit indices");
     const size_t mbytes = (size_t)n * n * 4;
-    Call call(data, len, 0, mbytes);
+    Call call(data, len, nullptr, 0, mbytes);
     if (!call.ok()) return call.err;
     uint32_t *m = reinterpret_cast<uint32_t *>(call.extra);
-    cudaError_t e = cudaMemsetAsync(m, 0, mbytes, call.s->stream);
+    cudaError_t e = cudaMemsetAsync(m, 0, mbytes, call.stream);
     if (e != cudaSuccess) return fail_cuda(e, "memset matrix");
     const uint64_t items = ((uint64_t)g.data_len + 15) / 16 + g.total_rows;
-    k_cooccurrence<<<grid_for(items, call.c->num_sms), RT, 0, call.s->stream>>>(call.d_in, g, n, m, call.st);
+    k_cooccurrence<<<grid_for(items, call.c->num_sms), RT, 0, call.stream>>>(call.d_in, g, n, m, call.st);
     if (int rc = call.check("k_cooccurrence")) return rc;
-    k_symmetrise<<<n, 256, 0, call.s->stream>>>(m, n);
+    k_symmetrise<<<n, 256, 0, call.stream>>>(m, n);
     if (int rc = call.check("k_symmetrise")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
     if (st.fail) return fail(OXI_E_ARG, "pixel index beyond the palette (run reduced_palette first, palette.rs:533-536)");
-    e = cudaMemcpyAsync(matrix, m, mbytes, cudaMemcpyDeviceToHost, call.s->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(call.s->stream);
-    return e == cudaSuccess ? OXI_OK : fail_cuda(e, "download matrix");
+    return call.to_host(matrix, m, mbytes);
 }
 
 } // extern "C"

@@ -1,4 +1,6 @@
-"""Host-side mirror of the reference's trial dispatch (src/evaluate.rs:24-201) over the fused GPU filter call.
+"""TEST / INTEGRATION EXAMPLE, not product code: a Python mirror of the reference's trial dispatch (src/evaluate.rs:24-201)
+over the fused GPU filter call.  In a real integration this control flow stays in the reference's Rust;
+it lives under tests/ so that the flow tests and bench.py's -o2 leg can drive the C ABI the way the reference would.
 
 The reference fans out `filters.par_iter()` -> `image.filter_image(filter, optimize_alpha)` -> `deflater.deflate(...)`
 on rayon workers (evaluate.rs:141-154).  Here all strategies of a candidate go to the GPU in ONE call
@@ -18,7 +20,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from .png import FilterStrategy, PngImage, filter_image_multi
+from oxipng_b200.png import FilterStrategy, PngImage, filter_image_multi
 
 _VARIANT = {"Basic": 0, "MinSum": 1, "Entropy": 2, "Bigrams": 3, "BigEnt": 4, "Brute": 5, "Predefined": 6}
 
@@ -73,7 +75,10 @@ class Evaluator:  # evaluate.rs:50-201
         nth = self.nth
         self.nth += 1
         # one fused GPU call for every strategy of this candidate (evaluate.rs:143-153 as a single launch)
-        outs, used = filter_image_multi(image, self.filters, self.optimize_alpha)
+        if hasattr(image, "filter_image_multi"):  # device-resident candidate (oxi_image_filter): only streams come back
+            outs, used = image.filter_image_multi(self.filters, self.optimize_alpha)
+        else:
+            outs, used = filter_image_multi(image, self.filters, self.optimize_alpha)
         kcs = key_chunks_size(image)
 
         def deflate(j):

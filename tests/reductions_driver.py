@@ -1,7 +1,8 @@
-"""Host-side mirror of `perform_reductions` (src/reduction/mod.rs:14-179): the ORDER and GATING of the reductions and
+"""TEST / INTEGRATION EXAMPLE, not product code (the control flow stays in the reference's Rust).
+Host-side mirror of `perform_reductions` (src/reduction/mod.rs:14-179): the ORDER and GATING of the reductions and
 which results go to the evaluator versus become the new baseline.  The control flow stays on the host exactly as in
 the reference; every pixel scan it calls runs on the GPU (oxipng_b200.reduction), every trial goes through the fused
-evaluator call (oxipng_b200.evaluate).
+evaluator call (tests/evaluate_mirror.py).
 
 `backend` is the module providing the reduction functions (default: oxipng_b200.reduction).  Tests pass an
 oracle-backed adapter with the same names to check end-to-end decision parity of the whole flow.
@@ -14,7 +15,7 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Optional
 
-from .png import PngImage, change_interlacing
+from oxipng_b200.png import PngImage, change_interlacing
 
 INDEXED_MAX_DIFF = 20000  # color.rs:16
 
@@ -38,7 +39,7 @@ def perform_reductions(png: PngImage, opts: Options, evaluator, backend=None, in
     """-> the baseline image (reduction/mod.rs:178); candidates that need a size comparison are pushed into `evaluator`
     with try_image, in the reference's order."""
     if backend is None:
-        from . import reduction as backend
+        from oxipng_b200 import reduction as backend
     R = backend
     evaluation_added = False
     cheap = opts.deflater_compression < 12 and opts.fast_evaluation  # :24-27

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 def test_evaluator_matches_oracle_driven_flow():
     import oxipng_b200 as ox
     from oxipng_b200 import reduction as R
-    from oxipng_b200.evaluate import Evaluator, key_chunks_size
+    from evaluate_mirror import Evaluator, key_chunks_size
     rng = np.random.default_rng(4)
     pal = rng.integers(0, 256, size=(40, 4), dtype=np.uint8)
     pal[:, 3] = 255

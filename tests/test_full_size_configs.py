@@ -128,3 +128,37 @@ def test_c4_reductions_2048():
     d16 = np.repeat(rgba, 2)
     r8 = R.reduced_bit_depth_16_to_8(helpers.product_image((2048, 2048, 6, 16, 0), d16), False)
     assert np.array_equal(r8.data, rgba)
+
+
+def test_c5_whole_images_none_bigrams_bigent():
+    """The headline workload itself: eight whole 1024x1024 RGBA8 images (two photographic, noisy, with all-zero rows, random)
+    through the fused {None, Bigrams, BigEnt} launch (k_fast<1, SC_BIGRAM|SC_HALF>), every filtered stream and every
+    per-row choice bit-exact against the oracle on all 8 x 1024 rows."""
+    import concurrent.futures as cf
+    import oxipng_b200 as ox
+    w = h = 1024
+    imgs = [_device_image(w, h, 4, 8, 0xB2000005 + i) for i in range(8)]
+    rng = np.random.default_rng(55)
+    for i, amp in ((2, 6), (3, 12), (4, 24)):  # extra noise on the colour channels: outlier hashes, flagged trials
+        nz = rng.integers(-amp, amp + 1, size=imgs[i].size)
+        nz[3::4] = 0
+        imgs[i] = ((imgs[i].astype(np.int64) + nz) & 255).astype(np.uint8)
+    imgs[5] = rng.integers(0, 256, size=imgs[5].size, dtype=np.uint8)  # every window an outlier, None competitive
+    imgs[6][: 40 * w * 4] = 0                                          # all-zero rows (png/mod.rs:398-404)
+    imgs[7] = np.repeat(rng.integers(0, 4, size=(h, w // 8, 4), dtype=np.uint8) * 60, 8, axis=1).reshape(-1)  # flat runs
+    hdr = ox.IhdrData(w, h, ox.ColorType.RGBA(), ox.BitDepth.Eight)
+    S = ox.FilterStrategy
+    outs, used = ox.filter_batch(hdr, np.concatenate(imgs), 8, [S.NONE, S.Bigrams, S.BigEnt], False)
+    per, rows = w * h * 4 + h, h
+    kinds = [(oracle.BASIC, 0), (oracle.BIGRAMS, 0), (oracle.BIGENT, 0)]
+    oracle.use_native()
+
+    def check(t):
+        i, j = t
+        want, want_used, _ = oracle.filter_image((w, h, 6, 8, 0), imgs[i], *kinds[j])
+        return (i, j, np.array_equal(used[j][i * rows:(i + 1) * rows], want_used),
+                np.array_equal(outs[j][i * per:(i + 1) * per], want))
+
+    with cf.ThreadPoolExecutor(max_workers=8) as ex:
+        for i, j, ok_used, ok_out in ex.map(check, [(i, j) for i in range(8) for j in range(3)]):
+            assert ok_used and ok_out, (i, j)

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _flow(case, backend, interlacer, **opt):
-    from oxipng_b200.reductions_driver import Options, perform_reductions
+    from reductions_driver import Options, perform_reductions
     img = helpers.product_image(case.ihdr, case.data, case.palette, case.trns)
     ev = helpers.RecordingEvaluator()
     base = perform_reductions(img, Options(**opt), ev, backend=backend, interlacer=interlacer)
