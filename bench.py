@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- filter-search throughput of the B200 path on BASELINE.json's batch configuration.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--images-per-gpu B] [--others]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--images-per-gpu B] [--no-others]
 
 Workload (config c5 of BASELINE.json): a batch of synthetic 1024x1024 RGBA8 images filtered with the -o4 strategy
 set that stays on the GPU, {None, Bigrams, BigEnt} (src/options.rs:220-233; Brute stays on the host), sharded by
@@ -346,9 +346,57 @@ def run_ours(args):
                          "C restatement of the reference (oracle/), gcc -O3 -march=native; "
                          "the Rust reference cannot be built in this image"}
 
+    # --- every other BASELINE configuration, driver-visible (rank 0; a few seconds of GPU time)
     others = None
-    if args.others and rank == 0:
-        others = run_other_configs(ox, synth, torch, dev, local, stream, args)
+    e2e_pageable = None
+    if not args.no_others and rank == 0 and world == 1:
+        import bench_extra as bx
+        peak_gbs, _ = peaks()
+        it = max(args.steps, 5)
+        others = {}
+        for part, fn in (("single", lambda: bx.single_image_configs(ox, synth, torch, dev, local, stream, peak_gbs, it)),
+                         ("batch", lambda: bx.batch_configs(ox, synth, torch, dev, local, stream, peak_gbs, it)),
+                         ("c4", lambda: {"c4_reductions_2048_256colours": bx.c4_reductions(ox, torch, dev, local, stream, peak_gbs)}),
+                         ("o2", lambda: {"o2_flow_resident_2048_256colours": bx.o2_flow(ox, torch, dev, local, stream)})):
+            try:
+                t0 = time.perf_counter()
+                others.update(fn())
+                log(f"[rank 0] other_configs/{part}: {time.perf_counter() - t0:.1f}s")
+            except Exception as e:  # a failing side record must not hide the headline line
+                others[f"{part}_error"] = repr(e)[:300]
+                log(f"[rank 0] other_configs/{part} failed: {e!r}")
+        if not args.no_e2e:
+            try:
+                e2e_pageable = bx.pageable_e2e(ox, torch, np, hdr, d_in, min(B, args.e2e_images), strategies, PER_IMAGE, ROWS,
+                                               max(2, args.steps // 3))
+            except Exception as e:
+                e2e_pageable = {"error": repr(e)[:300]}
+
+    # --- multi-GPU side records: what the host fabric gives the e2e path, and one huge image split into row bands
+    ceiling = None
+    band = None
+    if not args.no_others and not args.no_e2e:
+        import bench_extra as bx
+        try:
+            Be = min(B, args.e2e_images)
+            hp_in = torch.empty(Be * PER_IMAGE, dtype=torch.uint8, pin_memory=True)
+            hp_outs = [torch.empty(Be * (out_per + ROWS), dtype=torch.uint8, pin_memory=True) for _ in range(K)]
+            ceiling = bx.copy_ceiling(torch, dist, dev, hp_in, hp_outs, max(2, args.steps // 2))
+            ceiling["aggregate_GBps"] = ceiling["per_rank_GBps"] * world
+            ceiling["raw_pixel_GBps_if_copy_bound"] = Be * world * PER_IMAGE / ceiling["seconds_per_step"] / 1e9
+            if e2e is not None:
+                ceiling["e2e_fraction_of_copy_ceiling"] = e2e["value"] / ceiling["raw_pixel_GBps_if_copy_bound"]
+            del hp_in, hp_outs
+        except Exception as e:
+            ceiling = {"error": repr(e)[:300]}
+        if dist is not None:
+            dist.barrier()
+        if rank == 0:
+            try:
+                n_dev = min(world, torch.cuda.device_count())
+                band = bx.row_band(ox, torch, np, n_dev)
+            except Exception as e:
+                band = {"error": repr(e)[:300]}
 
     if rank == 0:
         line = {
@@ -362,60 +410,16 @@ def run_ours(args):
         }
         if others is not None:
             line["other_configs"] = others
+        if e2e_pageable is not None:
+            line["e2e_pageable"] = e2e_pageable
+        if ceiling is not None:
+            line["copy_ceiling"] = ceiling
+        if band is not None:
+            line["row_band"] = band
         emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def run_other_configs(ox, synth, torch, dev, local, stream, args):
-    """Kernel-only throughput of the single-image BASELINE configs c1-c3 (device-resident, L2 flushed between
-    iterations because these inputs are smaller than the 126 MB L2)."""
-    peak, _ = peaks()
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    res = {}
-    cfgs = [
-        ("c1_minsum_rgba8_4096", 4096, 4096, 4, 8, False, [ox.FilterStrategy.MinSum]),
-        ("c2_entropy_rgb8_8192", 8192, 8192, 3, 8, False, [ox.FilterStrategy.Entropy]),
-        ("c2_basic_paeth_rgb8_8192", 8192, 8192, 3, 8, False, [ox.FilterStrategy.PAETH]),
-        ("c2_basic_none_rgb8_8192", 8192, 8192, 3, 8, False, [ox.FilterStrategy.NONE]),
-        ("c3a_bigrams_rgba16_4096", 4096, 4096, 4, 16, False, [ox.FilterStrategy.Bigrams]),
-        ("c3a_bigent_rgba16_4096", 4096, 4096, 4, 16, False, [ox.FilterStrategy.BigEnt]),
-        ("c3b_bigrams_bigent_rgba8_4096_adam7", 4096, 4096, 4, 8, True, [ox.FilterStrategy.Bigrams, ox.FilterStrategy.BigEnt]),
-        ("bigrams_bigent_rgba8_4096", 4096, 4096, 4, 8, False, [ox.FilterStrategy.Bigrams, ox.FilterStrategy.BigEnt]),
-    ]
-    for name, w, h, ch, bd, il, strat in cfgs:
-        ct = {1: ox.ColorType.Grayscale(), 3: ox.ColorType.RGB(), 4: ox.ColorType.RGBA()}[ch]
-        hdr = ox.IhdrData(w, h, ct, ox.BitDepth(bd), il)
-        d = synth.photo_image(w, h, ch, bd, 0xB2000001, dev)
-        if il:  # the same picture in the Adam7 layout (oxi_interlace_image, interlace.rs:6-60)
-            prog = ox.PngImage(ox.IhdrData(w, h, ct, ox.BitDepth(bd), False), d.cpu().numpy())
-            d = torch.from_numpy(ox.interlace_image(prog).data.copy()).to(dev)
-        n = d.numel()
-        rows = int(ox.lib().oxi_num_scanlines(__import__("ctypes").byref(hdr._c()), n))
-        o = [torch.empty(n + rows, dtype=torch.uint8, device=dev) for _ in strat]
-        u = [torch.empty(rows, dtype=torch.uint8, device=dev) for _ in strat]
-
-        def step():
-            ox.filter_batch_device(local, stream.cuda_stream, hdr, d.data_ptr(), n, 1, strat, False,
-                                   [t.data_ptr() for t in o], [t.data_ptr() for t in u])
-        for _ in range(3):
-            step()
-        times = []
-        for _ in range(max(args.steps, 5)):
-            flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            step()
-            e1.record(stream)
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
-        ms = statistics.median(times)
-        alg = n + len(strat) * (n + 2 * rows)
-        res[name] = {"ms": ms, "raw_pixel_GBps": n / ms / 1e6, "algorithmic_GBps": alg / ms / 1e6,
-                     "frac_of_measured_hbm": alg / ms / 1e6 / peak, "l2": "flushed (512 MB fill) between iterations"}
-        del d, o, u
-    return res
 
 
 def main():
@@ -425,7 +429,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images-per-gpu", type=int, default=1250)
-    ap.add_argument("--others", action="store_true", help="also time the single-image configs c1-c3 (kernel only)")
+    ap.add_argument("--others", action="store_true", help="(default now) also time configs c1-c4, the -o2 set and flow")
+    ap.add_argument("--no-others", action="store_true", help="headline c5 line only")
     ap.add_argument("--e2e-images", type=int, default=256, help="images per rank and step in the end-to-end leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -114,6 +114,14 @@ int oxi_filter_batch_device(int device, void *stream, const oxi_ihdr *, const ui
                             size_t n_images, const oxi_strategy *strategies, size_t k, int optimize_alpha,
                             uint8_t *const *d_outs, uint8_t *const *d_filters_used, unsigned flags);
 
+/* One large image split into row bands with a one-row halo, the bands filtered concurrently on `devices`
+ * (png/mod.rs:375-378,422: with optimize_alpha off a row depends only on the previous raw row of its pass).  Host
+ * buffers; one worker thread and stream per device; about bands_per_device bands each.  optimize_alpha with an alpha
+ * channel makes rows serial: OXI_E_UNSUPPORTED. */
+int oxi_filter_image_sharded(const oxi_ihdr *, const uint8_t *data, size_t data_len, const oxi_strategy *strategies, size_t k,
+                             int optimize_alpha, const int *devices, int n_devices, int bands_per_device,
+                             uint8_t *const *outs, uint8_t *const *filters_used, unsigned flags);
+
 /* ---- reduction scans, src/reduction/{alpha,bit_depth,color,palette}.rs ----------------------- */
 /* Every function: host buffers in, host buffers out; `out` must hold the stated worst case.
  * out_ihdr / out_aux receive the IhdrData / ColorType payload of the returned image. */

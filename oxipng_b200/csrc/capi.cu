@@ -7,6 +7,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -367,6 +368,112 @@ int filter_resident(int device, cudaStream_t stream, const oxi_ihdr *h, const ui
     return rc;
 }
 
+// ---- one large image split into row bands across devices (png/mod.rs:375-378,422) ---------------------------
+// With optimize_alpha off a filtered row depends on its own bytes and on the previous RAW row of the same pass only, so a
+// band of rows needs a one-row halo and nothing else.  A band is run as a small non-interlaced image whose first row is
+// the halo (its output row is dropped); the bands' outputs are disjoint, contiguous ranges of the filtered stream.
+struct RowBand {
+    uint32_t pixels, len;   // of one scanline of the band's pass
+    uint32_t first_row, n_rows;
+    bool halo;
+    uint64_t in_begin, in_end;   // bytes of PngImage.data to ship (halo row included)
+    uint64_t out_begin;          // where the band's filtered rows start in the filtered stream
+};
+
+void split_bands(const Geom &g, size_t n_parts, std::vector<RowBand> *bands) {
+    for (uint32_t p = 0; p < g.n_pass; p++) {
+        const PassDesc &pd = g.pass[p];
+        const double frac = g.data_len ? (double)pd.nrows * pd.len / (double)g.data_len : 1.0;
+        size_t share = (size_t)(n_parts * frac + 0.5);
+        if (share < 1) share = 1;
+        if (share > pd.nrows) share = pd.nrows;
+        for (size_t b = 0; b < share; b++) {
+            const uint32_t k0 = (uint32_t)(b * pd.nrows / share), k1 = (uint32_t)((b + 1) * pd.nrows / share);
+            if (k1 <= k0) continue;
+            RowBand rb;
+            rb.pixels = pd.pixels;
+            rb.len = pd.len;
+            rb.first_row = pd.row0 + k0;
+            rb.n_rows = k1 - k0;
+            rb.halo = k0 > 0;
+            rb.in_begin = pd.in_base + (uint64_t)(k0 - (rb.halo ? 1 : 0)) * pd.len;
+            rb.in_end = pd.in_base + (uint64_t)k1 * pd.len;
+            rb.out_begin = pd.in_base + (uint64_t)k0 * pd.len + pd.row0 + k0;
+            bands->push_back(rb);
+        }
+    }
+}
+
+// all bands of one device, in order, on one pooled slot (called on that device's worker thread)
+int run_bands_on_device(int device, const oxi_ihdr *h, const uint8_t *data, const std::vector<RowBand> &bands, size_t b0,
+                        size_t b1, const oxi_strategy *st, size_t k, uint8_t *const *outs, uint8_t *const *used, unsigned flags,
+                        std::string *msg) {
+    int err = 0, rc = OXI_OK;
+    DeviceCtx *c = get_ctx(device, &err);
+    Slot *slot = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!c) rc = err;
+    if (rc == OXI_OK && (e = cudaSetDevice(device)) != cudaSuccess) rc = fail_cuda(e, "cudaSetDevice");
+    if (rc == OXI_OK && !(slot = acquire_slot(c))) rc = fail(OXI_E_CUDA, "cannot create stream");
+    if (rc == OXI_OK && (e = slot_begin(slot, slot->stream)) != cudaSuccess) rc = fail_cuda(e, "cudaStreamWaitEvent");
+    std::vector<std::vector<uint8_t>> pre(k); // Predefined lists re-based to the band (row i of the band = global row first_row + i)
+    for (size_t bi = b0; bi < b1 && rc == OXI_OK; bi++) {
+        const RowBand &b = bands[bi];
+        const uint32_t skip = b.halo ? 1 : 0, rows = b.n_rows + skip;
+        oxi_ihdr sub = *h;
+        sub.width = b.pixels;
+        sub.height = rows;
+        sub.interlaced = 0;
+        Geom g;
+        if (!build_geom(&sub, (size_t)(b.in_end - b.in_begin), 0, &g) || g.total_rows != rows || g.pass[0].len != b.len) {
+            rc = fail(OXI_E_ARG, "band geometry");
+            break;
+        }
+        std::vector<oxi_strategy> bst(st, st + k);
+        for (size_t j = 0; j < k; j++) {
+            if (st[j].kind != OXI_PREDEFINED) continue;
+            pre[j].assign(rows, 0);
+            for (uint32_t i = 0; i < b.n_rows; i++)
+                if ((size_t)b.first_row + i < st[j].n_predefined) pre[j][skip + i] = st[j].predefined[b.first_row + i];
+            bst[j].predefined = pre[j].data();
+            bst[j].n_predefined = rows;
+        }
+        if (bi > b0) { // the slot's buffers (and `pre`) are still in use by the previous band
+            if ((e = cudaStreamSynchronize(slot->stream)) != cudaSuccess) { rc = fail_cuda(e, "cudaStreamSynchronize"); break; }
+        }
+        if ((e = grow(&slot->d_in, &slot->in_cap, (size_t)g.data_len + 64)) != cudaSuccess) { rc = fail_cuda(e, "cudaMalloc(input)"); break; }
+        const size_t out_stride = ((size_t)g.out_len + 255) & ~(size_t)255, used_stride = ((size_t)rows + 255) & ~(size_t)255;
+        if ((e = grow(&slot->d_out, &slot->out_cap, k * (out_stride + used_stride) + 64)) != cudaSuccess) { rc = fail_cuda(e, "cudaMalloc(output)"); break; }
+        uint8_t *d_outs[MAX_STRATEGIES], *d_used[MAX_STRATEGIES];
+        for (size_t j = 0; j < k; j++) {
+            d_outs[j] = slot->d_out + j * (out_stride + used_stride);
+            d_used[j] = d_outs[j] + out_stride;
+        }
+        StrategySet set;
+        if ((rc = make_set(slot, slot->stream, bst.data(), k, d_outs, d_used, &set)) != OXI_OK) break;
+        if ((e = cudaMemcpyAsync(slot->d_in, data + b.in_begin, (size_t)g.data_len, cudaMemcpyHostToDevice, slot->stream)) != cudaSuccess) {
+            rc = fail_cuda(e, "cudaMemcpyAsync(H2D band)");
+            break;
+        }
+        if ((rc = run_filters(c, slot, slot->stream, g, slot->d_in, 1, set, flags)) != OXI_OK) break;
+        const size_t band_out = (size_t)b.n_rows * (b.len + 1u);
+        for (size_t j = 0; j < k && e == cudaSuccess; j++) {
+            if (outs && outs[j])
+                e = cudaMemcpyAsync(outs[j] + b.out_begin, d_outs[j] + (size_t)skip * (b.len + 1u), band_out, cudaMemcpyDeviceToHost, slot->stream);
+            if (e == cudaSuccess && used && used[j])
+                e = cudaMemcpyAsync(used[j] + b.first_row, d_used[j] + skip, b.n_rows, cudaMemcpyDeviceToHost, slot->stream);
+        }
+        if (e != cudaSuccess) rc = fail_cuda(e, "cudaMemcpyAsync(D2H band)");
+    }
+    if (slot) {
+        e = cudaStreamSynchronize(slot->stream);
+        if (e != cudaSuccess && rc == OXI_OK) rc = fail_cuda(e, "cudaStreamSynchronize");
+        release_slot(c, slot);
+    }
+    if (rc != OXI_OK && msg) *msg = t_err;
+    return rc;
+}
+
 } // namespace oxi
 
 using namespace oxi;
@@ -509,6 +616,41 @@ int oxi_filter_batch(const oxi_ihdr *h, const uint8_t *data, size_t data_len, si
         release_slot(c, slots[i]);
     }
     return rc;
+}
+
+int oxi_filter_image_sharded(const oxi_ihdr *h, const uint8_t *data, size_t data_len, const oxi_strategy *strategies, size_t k,
+                             int optimize_alpha, const int *devices, int n_devices, int bands_per_device, uint8_t *const *outs,
+                             uint8_t *const *filters_used, unsigned flags) {
+    Geom g;
+    if (!build_geom(h, data_len, optimize_alpha, &g)) return fail(OXI_E_ARG, "invalid IHDR");
+    if (!data || !strategies || k == 0 || k > (size_t)MAX_STRATEGIES || !devices || n_devices < 1 || n_devices > 64)
+        return fail(OXI_E_ARG, "bad arguments");
+    for (size_t j = 0; j < k; j++)
+        if (!valid_strategy(&strategies[j])) return fail(OXI_E_ARG, "invalid strategy");
+    // with optimize_alpha the next row is filtered against the winning trial's rewritten row (png/mod.rs:412-423):
+    // rows are serial and the image cannot be split
+    if (g.alpha_bytes != 0) return fail(OXI_E_UNSUPPORTED, "optimize_alpha makes rows serially dependent: no row-band sharding");
+    if (g.total_rows == 0) return OXI_OK;
+    if (bands_per_device < 1) bands_per_device = 1;
+    std::vector<RowBand> bands;
+    split_bands(g, (size_t)n_devices * bands_per_device, &bands);
+    // contiguous runs of bands per device, one worker thread each (pageable host memory makes cudaMemcpyAsync
+    // synchronous for the issuing thread, so the devices are driven from separate threads)
+    const size_t nb = bands.size();
+    std::vector<int> rcs(n_devices, OXI_OK);
+    std::vector<std::string> msgs(n_devices);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < n_devices; d++) {
+        const size_t b0 = nb * d / n_devices, b1 = nb * (d + 1) / n_devices;
+        if (b0 == b1) continue;
+        workers.emplace_back([&, d, b0, b1] {
+            rcs[d] = run_bands_on_device(devices[d], h, data, bands, b0, b1, strategies, k, outs, filters_used, flags, &msgs[d]);
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (int d = 0; d < n_devices; d++)
+        if (rcs[d] != OXI_OK) return fail(rcs[d], msgs[d].c_str());
+    return OXI_OK;
 }
 
 int oxi_filter_image_multi(const oxi_ihdr *h, const uint8_t *data, size_t data_len, const oxi_strategy *strategies,

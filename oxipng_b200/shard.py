@@ -61,26 +61,41 @@ def row_bands(scan_lines: Sequence[tuple], n_parts: int) -> List[Band]:
     return bands
 
 
+def filter_image_sharded(png, strategies, devices: Sequence[int] = (0,), bands_per_device: int = 1, flags: int = 0,
+                         outs=None, used=None):
+    """oxi_filter_image_sharded: one large image split into row bands (one-row halo), the bands filtered concurrently on
+    `devices` -- one worker thread and stream per device inside the C library.  optimize_alpha is off by construction.
+    -> ([filtered stream per strategy], [filters_used per strategy])"""
+    import ctypes as C
+    from ._lib import CStrategy, check, lib
+    L = lib()
+    L.oxi_filter_image_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(CStrategy), C.c_size_t, C.c_int,
+                                           C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_void_p), C.c_uint]
+    d = np.ascontiguousarray(png.data, dtype=np.uint8)
+    h = png.ihdr._c()
+    rows = L.oxi_num_scanlines(C.byref(h), d.size)
+    k = len(strategies)
+    cs = (CStrategy * k)()
+    keep = []
+    for j, s in enumerate(strategies):
+        cs[j], ka = s._c()
+        keep.append(ka)
+    if outs is None:
+        outs = [np.empty(d.size + rows, dtype=np.uint8) for _ in range(k)]
+    if used is None:
+        used = [np.empty(rows, dtype=np.uint8) for _ in range(k)]
+    po = (C.c_void_p * k)(*[o.ctypes.data for o in outs])
+    pu = (C.c_void_p * k)(*[u.ctypes.data for u in used])
+    devs = (C.c_int * len(devices))(*devices)
+    check(L.oxi_filter_image_sharded(C.byref(h), C.c_void_p(d.ctypes.data), d.size, cs, k, 0, devs, len(devices),
+                                     int(bands_per_device), po, pu, flags), "oxi_filter_image_sharded")
+    return outs, used
+
+
 def filter_image_banded(png, strategy, n_parts: int, devices: Sequence[int] = (0,)):
-    """filter_image of one large image split into row bands, band b on devices[b % len(devices)].
-    optimize_alpha must be off (rows are serially dependent otherwise).  -> (filtered stream, filters_used)"""
-    from . import png as P
-    from ._lib import check, lib
-    lines = png.scan_lines()
-    bands = row_bands(lines, n_parts)
-    out = np.empty(png.data.size + len(lines), dtype=np.uint8)
-    used = np.empty(len(lines), dtype=np.uint8)
-    for bi, b in enumerate(bands):
-        check(lib().oxi_set_device(devices[bi % len(devices)]), "oxi_set_device")
-        rows = b.n_rows + (1 if b.has_halo else 0)
-        sub = P.PngImage(P.IhdrData(b.width_px, rows, png.ihdr.color_type, png.ihdr.bit_depth, False),
-                         png.data[b.in_begin:b.in_end])
-        strat = strategy
-        if strategy.kind == "Predefined":  # row i of the band is global row first_row + i
-            lines_ = list(strategy.lines[b.first_row:b.first_row + b.n_rows])
-            strat = P.FilterStrategy.Predefined(([0] if b.has_halo else []) + lines_)
-        o, u = P.filter_image_multi(sub, [strat], False)
-        skip = 1 if b.has_halo else 0
-        out[b.out_begin:b.out_end] = o[0][skip * (b.row_len + 1):]
-        used[b.first_row:b.first_row + b.n_rows] = u[0][skip:]
-    return out, used
+    """filter_image of one large image split into about n_parts row bands over `devices` (concurrently; see
+    filter_image_sharded).  -> (filtered stream, filters_used)"""
+    per = max(1, -(-n_parts // max(len(devices), 1)))
+    outs, used = filter_image_sharded(png, [strategy], devices, per)
+    return outs[0], used[0]

@@ -118,3 +118,26 @@ def test_banded_filtering_on_gpu_matches_oracle():
             want, want_used, _ = oracle.filter_image(ih, d, kind, basic)
             out, used = shard.filter_image_banded(img, helpers.product_strategy(name), 5)
             assert np.array_equal(out, want) and np.array_equal(used, want_used), (il, name)
+
+
+@pytest.mark.gpu
+def test_sharded_c_abi_multi_strategy_and_predefined():
+    """oxi_filter_image_sharded: several strategies per call, Predefined lists re-based per band, every visible device."""
+    import torch
+    import oxipng_b200 as ox
+    devices = list(range(min(torch.cuda.device_count(), 8)))
+    for il in (False, True):
+        ih, d = helpers.synth_image(700, 150, 6, 8, 12, "photo", il)
+        img = helpers.product_image(ih, d)
+        rows = len(img.scan_lines())
+        pre = [(i * 7) % 5 for i in range(rows)]
+        names = ["None", "Paeth", "MinSum", "Entropy", "Bigrams", "BigEnt"]
+        strat = [helpers.product_strategy(n) for n in names] + [ox.FilterStrategy.Predefined(pre)]
+        for per in (1, 3):
+            outs, used = shard.filter_image_sharded(img, strat, devices, per)
+            kinds = {n: (k, b) for n, k, b in helpers.STRATEGIES}
+            for n, o, u in zip(names, outs, used):
+                want, want_used, _ = oracle.filter_image(ih, d, *kinds[n])
+                assert np.array_equal(u, want_used) and np.array_equal(o, want), (il, per, n)
+            want, want_used, _ = oracle.filter_image(ih, d, oracle.PREDEFINED, 0, pre)
+            assert np.array_equal(used[-1], want_used) and np.array_equal(outs[-1], want), (il, per, "Predefined")
