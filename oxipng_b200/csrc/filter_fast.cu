@@ -51,7 +51,7 @@ struct FastParams {
     uint32_t shift; // 8 * (bpp % 4): funnel-shift amount that turns a row word into its "left" word
     uint32_t nslot;     // ring slots (4 when shared memory allows: removes the end-of-row barrier; else 3)
     uint32_t h0_slots;  // bigram scorer with small_tab: slots of the trial-0 hash table (power of two, > 2 * row bytes)
-    uint32_t small_tab; // bigram scorer: the dense-table layout is carved (rows <= 16384 bytes)
+    uint32_t small_tab; // bigram scorer: 1 = the dense-table layout (rows <= 16384 bytes), 2 = the split-table layout (<= 32768)
 };
 
 __host__ __device__ constexpr int threads_for(int sc) { return (sc & SC_HALF) ? HALF_NT : (sc & SC_BIGRAM) ? 1024 : sc == SC_ENTROPY ? 512 : 256; }
@@ -216,9 +216,20 @@ constexpr uint32_t SMALL_BYTES = DENSE_WORDS * 4 + 4 * HSLOTS * 4; // dense tabl
 // h0_slots != 0 selects the small-table layout: header | histograms | dense tables | outlier hashes | h0 | row ring.
 // The tables come first so that their shared-memory offsets are compile-time constants (immediates of the atomics).
 // Otherwise: header | histograms | row ring | 65536-entry bigram table.
+constexpr uint32_t SPLIT_SET = 65536;    // split layout: bytes of one table set -- A (32 x 256 u32), then B (256 x 32 u32)
+constexpr uint32_t SPLIT_OSLOTS = 128;   // slots of a set's outlier hash
+constexpr uint32_t SPLIT_BYTES = 2 * SPLIT_SET + 2 * SPLIT_OSLOTS * 4;
 template <int SC>
-__device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot, uint32_t h0_slots) {
+__device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot, uint32_t h0_slots, bool split = false) {
     Smem s;
+    if (split) { // header | two table sets (= the 65536 x u16 table of the exact trials) | two outlier hashes | row ring
+        s.bar = reinterpret_cast<uint64_t *>(base);
+        s.sc = reinterpret_cast<uint32_t *>(base + 64);
+        s.hist = s.small = s.table = reinterpret_cast<uint32_t *>(base + SMEM_HDR);
+        s.ohash = s.table + 2 * SPLIT_SET / 4;
+        s.rows = base + SMEM_HDR + SPLIT_BYTES;
+        return s;
+    }
     s.bar = reinterpret_cast<uint64_t *>(base);
     uint32_t *u = reinterpret_cast<uint32_t *>(base + 64);
     s.sc = u; // set 0; sets 1 and 2 follow at SCORE_WORDS strides
@@ -238,7 +249,8 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot
     return s;
 }
 // h0_slots != 0: the small-table layout (hash of whole rows + dense tables + outlier hashes); 0: the 65536-entry table
-__host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, uint32_t h0_slots, uint32_t nslot = 3) {
+__host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, uint32_t h0_slots, uint32_t nslot = 3, bool split = false) {
+    if (split) return SMEM_HDR + SPLIT_BYTES + nslot * rb;
     uint32_t b = SMEM_HDR + nslot * rb;
     if (sc & SC_ENTROPY) b += 5 * HIST_REP * 256 * 4;
     if (sc & SC_BIGRAM) b += h0_slots ? ((sc & SC_HALF) ? 0u : h0_slots * 4) + SMALL_BYTES : 65536 * 2;
@@ -885,6 +897,193 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
     return nz;
 }
 
+// ---- Bigrams/BigEnt for rows of 16 KB .. 32 KB (split tables) ---------------------------------------------------------
+// Rows this long are mostly 16-bit images, whose low bytes are noise: almost no window has BOTH residuals near zero, so
+// the 32 x 32 tables above would count nothing, and the 65536-entry table of `bigram_trial` (u16 counters, returning
+// atomics, two passes per trial) ran at 2.7 % of the roofline.  Here a window (a, b) of trial F -- as range codes
+// residual + 16 -- is counted
+//     in table A[a][b ^ a]        (32 x 256 u32)  when a < 32 (first residual in [-16, 15]), else
+//     in table B[a][(b ^ a) & 31] (256 x 32 u32)  when b < 32,
+//     else in a small hash (both far from zero: the first pixels of a row, edges).
+// Every key has exactly one home, so sweeping A, B and the hash gives the exact distinct count and sum of ilog2i(count).
+// Trial 0 (raw bytes) uses a = byte & 31 for every window: keys merge, which bounds its scores (see bigram_row_small);
+// if the bounds leave open that None wins, or a trial's hash overflows, that trial is recounted exactly by
+// `bigram_trial` in the same memory (the table sets are clean between trials).  The trials run one after the other
+// on two alternating table sets: while the CTA counts trial F+1 into one set it sweeps trial F out of the other, with
+// one CTA-wide barrier per trial.
+__device__ __noinline__ void split_outlier(uint32_t key, uint32_t F, uint32_t ohash_addr, uint32_t s_out_addr) {
+    volatile uint32_t *s_out = reinterpret_cast<volatile uint32_t *>(__cvta_shared_to_generic(s_out_addr));
+    if (s_out[F]) return;
+    uint32_t *h = reinterpret_cast<uint32_t *>(__cvta_shared_to_generic(ohash_addr));
+    uint32_t s = ((key * 40503u) >> 6) & (SPLIT_OSLOTS - 1);
+    for (int probe = 0; probe < HPROBE; probe++) {
+        uint32_t cur = *(volatile uint32_t *)&h[s];
+        if (cur == 0) {
+            cur = atomicCAS(&h[s], 0u, (key << 16) | 1u);
+            if (cur == 0) return;
+        }
+        if ((cur >> 16) == key) {
+            atomicAdd(&h[s], 1u);
+            return;
+        }
+        s = (s + 1) & (SPLIT_OSLOTS - 1);
+    }
+    s_out[F] = 1u; // crowded: the trial is recounted exactly
+}
+
+// Counts trial F of the row into the table set at shared-window address TB (its outlier hash at ohash_addr).
+// Returns the OR of this thread's row bytes.
+template <int D, int NT, int F, uint32_t TB>
+__device__ __forceinline__ uint32_t split_count(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
+                                                uint32_t ohash_addr, uint32_t s_out_addr) {
+    const uint32_t nwords = (len + 3) >> 2, lane = threadIdx.x & 31u;
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(cur), *uw = reinterpret_cast<const uint32_t *>(up);
+    uint32_t nz = 0;
+    for (uint32_t k = threadIdx.x; k < ((nwords + 31u) & ~31u); k += NT) {
+        const int kk = (int)k;
+        uint32_t t = 0, x = 0;
+        if (k < nwords) {
+            // row words k-1-D .. k are addressable: the slot has 32 zero bytes in front of the row
+            uint32_t l = 0, u = 0, ul = 0;
+            x = cw[kk];
+            if (F == 1 || F == 3 || F == 4)
+                l = D == 2 ? cw[kk - 2] : D == 1 ? __funnelshift_l(cw[kk - 2], cw[kk - 1], shift)
+                                                 : __funnelshift_l(cw[kk - 1], cw[kk], shift);
+            if (F >= 2) u = uw[kk];
+            if (F == 4)
+                ul = D == 2 ? uw[kk - 2] : D == 1 ? __funnelshift_l(uw[kk - 2], uw[kk - 1], shift)
+                                                  : __funnelshift_l(uw[kk - 1], uw[kk], shift);
+            t = F == 0 ? x : __vsub4(__vadd4(x, 0x10101010u), pred4<F>(l, u, ul)); // range codes (raw bytes for trial 0)
+        }
+        // code of the stream byte in front of this word: the neighbouring lane's last byte; lane 0: the filter id in front
+        // of word 0, else one scalar pixel
+        uint32_t p = __shfl_up_sync(0xffffffffu, t >> 24, 1);
+        if (lane == 0)
+            p = k == 0 ? (F == 0 ? 0u : (uint32_t)F + 16u)
+                       : (k < nwords ? ((residual_at(F, cur, up, 4 * kk - 1, bpp) + (F == 0 ? 0u : 16u)) & 255u) : 0u);
+        if (k >= nwords) continue;
+        const int valid = (int)len - 4 * kk; // >= 1
+        if (F == 0) nz |= valid >= 4 ? x : (x & tail_mask(valid));
+        const uint32_t cb = t;
+        const uint32_t ca = prmt(t, p, 0x2104u); // byte m: m ? t.byte[m-1] : p
+        const uint32_t caA = ca & 0x1F1F1F1Fu;   // first code as a table-A index (trial 0: the coarse first byte itself)
+        const uint32_t cbx = cb ^ caA;           // only the low five bits of b change: a bijection per a
+        // A: offset a << 10 | (b ^ a) << 2       -> high byte a << 2 | (b ^ a) >> 6, low byte ((b ^ a) & 63) << 2
+        // B: offset a << 7 | ((b ^ a) & 31) << 2 -> high byte a >> 1,                low byte (a & 1) << 7 | ((b ^ a) & 31) << 2
+        // Both sets of address bytes are formed for the whole word and merged bytewise by "a < 32".  The instruction's
+        // immediate is the set's address + 0x8000 and the high byte carries bit 7 inverted: prmt's sign replication then
+        // yields (offset - 0x8000) for A and (offset + 0x8000 - 0x8000) + 0x8000 - 0x8000 ... i.e. A lands in the first
+        // 32 KB of the set and B in the second.
+        const uint32_t sh2 = cbx << 2;
+        const uint32_t hiA = caA * 4u + (((cbx >> 6) & 0x03030303u) | 0x80808080u), loA = sh2 & 0xFCFCFCFCu;
+        const uint32_t hiB = (ca >> 1) & 0x7F7F7F7Fu, loB = ((ca & 0x01010101u) << 7) | (sh2 & 0x7C7C7C7Cu);
+        uint32_t hi = hiA, lo = loA, outl = 0;
+        if (F != 0) {
+            const uint32_t zA = ca & 0xE0E0E0E0u, zB = cb & 0xE0E0E0E0u;
+            const uint32_t nzA = (zA | (zA << 1) | (zA << 2)) & 0x80808080u; // 0x80 in every byte with a >= 32
+            const uint32_t nzB = (zB | (zB << 1) | (zB << 2)) & 0x80808080u;
+            const uint32_t mB = signmask4(nzA);                              // 0xFF where the window goes to B (or nowhere)
+            hi = (hiA & ~mB) | (hiB & mB);
+            lo = (loA & ~mB) | (loB & mB);
+            outl = nzA & nzB; // windows with both residuals far from zero
+        }
+        if (valid >= 4 && outl == 0) {
+            smem_inc_at<TB + 0x8000u>(prmt(lo, hi, 0xCC40u));
+            smem_inc_at<TB + 0x8000u>(prmt(lo, hi, 0xDD51u));
+            smem_inc_at<TB + 0x8000u>(prmt(lo, hi, 0xEE62u));
+            smem_inc_at<TB + 0x8000u>(prmt(lo, hi, 0xFF73u));
+        } else {
+            for (int j = 0; j < 4 && j < valid; j++) {
+                const uint32_t hb = (hi >> (8 * j)) & 255u, lb = (lo >> (8 * j)) & 255u;
+                if ((outl >> (8 * j)) & 0x80u)
+                    split_outlier((((ca >> (8 * j)) & 255u) << 8) | ((cb >> (8 * j)) & 255u), (uint32_t)F, ohash_addr, s_out_addr);
+                else
+                    smem_inc(TB + 0x8000u + (uint32_t)(((int32_t)(int8_t)hb) * 256) + lb);
+            }
+        }
+    }
+    return nz;
+}
+
+// Sweeps (and clears) one table set and its outlier hash: the scores of trial f are added to s_bgc[f] / s_bge[f] -- unless
+// the trial is flagged (its hash overflowed): then the set is only cleared and the trial is recounted exactly later.
+template <int NT>
+__device__ __forceinline__ void split_sweep(uint32_t *set, uint32_t *oh, uint32_t f, const Smem &sr) {
+    uint4 *s4 = reinterpret_cast<uint4 *>(set);
+    uint32_t d = 0, e = 0;
+    for (uint32_t q = threadIdx.x; q < SPLIT_SET / 16; q += NT) {
+        const uint4 a = s4[q];
+        if (a.x | a.y | a.z | a.w) {
+            s4[q] = make_uint4(0, 0, 0, 0);
+            d += (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0);
+            e += ilog2i_z(a.x) + ilog2i_z(a.y) + ilog2i_z(a.z) + ilog2i_z(a.w);
+        }
+    }
+    if (threadIdx.x < SPLIT_OSLOTS) {
+        const uint32_t v = oh[threadIdx.x];
+        if (v) {
+            oh[threadIdx.x] = 0;
+            d += 1;
+            e += ilog2i(v & 0xFFFFu);
+        }
+    }
+    d = warp_sum(d);
+    e = warp_sum(e);
+    if ((threadIdx.x & 31) == 0 && d && sr.s_out_()[f] == 0) {
+        atomicAdd(&sr.s_bgc_()[f], d);
+        atomicAdd(&sr.s_bge_()[f], e);
+    }
+}
+
+// One row.  Returns "some byte of the row is non-zero"; on return the scores of all five trials are final in
+// s_bgc / s_bge (exact, trial 0 included if the strategies need it) and every thread is behind a barrier.
+template <int D, int NT>
+__device__ __forceinline__ bool bigram_row_split(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
+                                                 const Smem &sr, bool want_bg, bool want_be) {
+    constexpr uint32_t T0 = SMEM_WIN + SMEM_HDR, T1 = T0 + SPLIT_SET, O0 = T0 + 2 * SPLIT_SET, O1 = O0 + SPLIT_OSLOTS * 4;
+    uint32_t *set0 = sr.table, *set1 = sr.table + SPLIT_SET / 4, *oh0 = sr.ohash, *oh1 = sr.ohash + SPLIT_OSLOTS;
+    const uint32_t so = smem_u32(sr.s_out_());
+    const uint32_t nz = split_count<D, NT, 0, T0>(cur, up, len, shift, bpp, O0, so);
+    const bool hz = __syncthreads_or(nz != 0) != 0;
+    split_count<D, NT, 1, T1>(cur, up, len, shift, bpp, O1, so);
+    split_sweep<NT>(set0, oh0, 0, sr);
+    __syncthreads();
+    split_count<D, NT, 2, T0>(cur, up, len, shift, bpp, O0, so);
+    split_sweep<NT>(set1, oh1, 1, sr);
+    __syncthreads();
+    split_count<D, NT, 3, T1>(cur, up, len, shift, bpp, O1, so);
+    split_sweep<NT>(set0, oh0, 2, sr);
+    __syncthreads();
+    split_count<D, NT, 4, T0>(cur, up, len, shift, bpp, O0, so);
+    split_sweep<NT>(set1, oh1, 3, sr);
+    __syncthreads();
+    split_sweep<NT>(set0, oh0, 4, sr);
+    __syncthreads();
+    if (!hz) return false; // all-zero row: None, whatever the scores (png/mod.rs:398-404)
+    // exact recounts, in the memory of the (clean) table sets: flagged trials, and trial 0 when its bounds do not rule it out
+    uint32_t *bc = sr.s_bgc_(), *be = sr.s_bge_();
+    const uint32_t wpt = (((len + 3) >> 2) + NT - 1) / NT;
+    for (int f = 1; f < 5; f++) {
+        if (sr.s_out_()[f] == 0) continue; // uniform
+        // (the sweeps added nothing for a flagged trial)
+        if (f == 1) { if (wpt <= 4) bigram_trial<D, NT, 1, 4>(cur, up, len, shift, bpp, sr.table, bc, be); else bigram_trial<D, NT, 1, 8>(cur, up, len, shift, bpp, sr.table, bc, be); }
+        if (f == 2) { if (wpt <= 4) bigram_trial<D, NT, 2, 4>(cur, up, len, shift, bpp, sr.table, bc, be); else bigram_trial<D, NT, 2, 8>(cur, up, len, shift, bpp, sr.table, bc, be); }
+        if (f == 3) { if (wpt <= 4) bigram_trial<D, NT, 3, 4>(cur, up, len, shift, bpp, sr.table, bc, be); else bigram_trial<D, NT, 3, 8>(cur, up, len, shift, bpp, sr.table, bc, be); }
+        if (f == 4) { if (wpt <= 4) bigram_trial<D, NT, 4, 4>(cur, up, len, shift, bpp, sr.table, bc, be); else bigram_trial<D, NT, 4, 8>(cur, up, len, shift, bpp, sr.table, bc, be); }
+    }
+    const uint32_t dmin = min(min(bc[1], bc[2]), min(bc[3], bc[4]));
+    const int32_t emax = max(max((int32_t)be[1], (int32_t)be[2]), max((int32_t)be[3], (int32_t)be[4]));
+    const bool n0 = (want_bg && bc[0] <= dmin) || (want_be && (int32_t)be[0] >= emax); // uniform
+    if (n0) {
+        __syncthreads(); // everybody has read the bounds
+        if (threadIdx.x == 0) { bc[0] = 0; be[0] = 0; }
+        __syncthreads();
+        if (wpt <= 4) bigram_trial<D, NT, 0, 4>(cur, up, len, shift, bpp, sr.table, bc, be);
+        else bigram_trial<D, NT, 0, 8>(cur, up, len, shift, bpp, sr.table, bc, be);
+    }
+    return true;
+}
+
 // ---- writing the chosen row --------------------------------------------------------------------------------------
 // out_row points at the filter-type byte of this row in the filtered stream.  Interior 16-byte granules of the
 // output are produced in the output's alignment frame; the (at most 31) edge bytes are written one by one.
@@ -989,7 +1188,8 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (
     constexpr int NT = threads_for(SC);
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t NS = P.nslot;
-    const Smem sm = carve<SC>(smem_raw, P.rb, NS, P.small_tab ? P.h0_slots : 0u);
+    const bool split = SC == SC_BIGRAM && P.small_tab == 2u;
+    const Smem sm = carve<SC>(smem_raw, P.rb, NS, P.small_tab == 1u ? P.h0_slots : 0u, split);
     const int tid = threadIdx.x;
     const int bpp = (int)P.g.bpp;
     const uint32_t shift = P.shift;
@@ -1005,8 +1205,8 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (
     if (SC & SC_ENTROPY)
         for (uint32_t i = tid; i < 5 * HIST_REP * 256; i += NT) sm.hist[i] = 0;
     if (SC & SC_BIGRAM) {
-        for (uint32_t i = tid; i < (P.small_tab ? P.h0_slots : 32768u); i += NT) sm.table[i] = 0;
-        if (P.small_tab)
+        for (uint32_t i = tid; i < (P.small_tab == 1u ? P.h0_slots : split ? SPLIT_BYTES / 4 : 32768u); i += NT) sm.table[i] = 0;
+        if (P.small_tab == 1u)
             for (uint32_t i = tid; i < SMALL_BYTES / 4; i += NT) sm.small[i] = 0;
     }
     __syncthreads();
@@ -1022,7 +1222,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (
     }
     // With a 4-slot ring a slot is refilled two iterations after its last reader, and every scored row contains at
     // least one CTA-wide barrier, so the end-of-row barrier is only needed for the 3-slot ring / unscored rows.
-    const bool defer_pf = (SC & SC_BIGRAM) && ((SC & SC_HALF) || P.small_tab) && any_heur && NS < 4;
+    const bool defer_pf = (SC & SC_BIGRAM) && ((SC & SC_HALF) || P.small_tab == 1u) && any_heur && NS < 4;
     const bool row_end_barrier = (NS < 4 && !defer_pf) || SC == 0 || !any_heur;
 
     for (uint64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -1104,7 +1304,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (
             if (SC != 0 && any_heur) {
                 if (tid < (int)SCORE_WORDS) sm.sc[set_next * SCORE_WORDS + tid] = 0;
                 uint32_t nz = 0;
-                bool small_flow = false;
+                bool small_flow = false, split_done = false;
                 if (SC & SC_MINSUM) minsum_pass<D, NT>(cur, up, len, shift, sr.s_min_());
                 if (SC & SC_ENTROPY) {
                     entropy_pass<D, NT>(cur, up, len, shift, sm.hist);
@@ -1113,7 +1313,11 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (
                 }
                 if (SC & SC_BIGRAM) {
                     const uint32_t wpt = (((len + 3) >> 2) + NT - 1) / NT; // row words per thread
-                    if ((SC & SC_HALF) || P.small_tab) {
+                    if (SC == SC_BIGRAM && split) {
+                        heur = bigram_row_split<D, NT>(cur, up, len, shift, bpp, sr, want_bg, want_be);
+                        split_done = true;
+                    }
+                    else if ((SC & SC_HALF) || P.small_tab == 1u) {
                         nz |= bigram_row_small<D, NT, SMEM_WIN + SMEM_HDR + ((SC & SC_ENTROPY) ? 5u * HIST_REP * 256u * 4u : 0u)>(cur, up, len, shift, bpp, sr, P.h0_slots, pf);
                         small_flow = true;
                     }
@@ -1159,7 +1363,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (
                         __syncthreads();
                     }
                     decided = true;
-                } else {
+                } else if (!split_done) {
                     // all-zero rows short-circuit to None (png/mod.rs:398-404); decided at the scorers' last barrier
                     if (SC & SC_MINSUM) { // S_0 = 128 per byte iff every byte is zero (see minsum_chunk)
                         __syncthreads();
@@ -1293,6 +1497,9 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
     while (h0 < 2 * g.max_len) h0 *= 2;
     P.small_tab = (sc & SC_BIGRAM) && g.max_len <= 16384 && smem_bytes_for(sc, P.rb, h0) <= SMEM_LIMIT;
     P.h0_slots = P.small_tab ? h0 : 0;
+    // longer rows (<= 32 KB; mostly 16-bit images): the split-table layout, see bigram_row_split
+    const bool split = sc == SC_BIGRAM && !P.small_tab && g.max_len <= 32768 && smem_bytes_for(sc, P.rb, 0, 3, true) <= SMEM_LIMIT;
+    if (split) P.small_tab = 2;
     // ... and with rows <= 4096 bytes two 512-thread CTAs fit an SM (two rows in flight: one CTA's barriers and table
     // sweeps overlap the other's counting)
     const uint32_t two_per_sm = (233472u / HALF_OCC - 1024u) & ~127u; // shared memory of one of HALF_OCC resident CTAs
@@ -1300,8 +1507,8 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
     const int nt = threads_for(sc);
     // a fourth ring slot removes the end-of-row barrier; take it when it does not cost occupancy (rows <= 16 KB)
     const uint32_t budget = (sc & SC_HALF) ? two_per_sm : SMEM_LIMIT;
-    P.nslot = (sc != 0 && P.rb <= 16448 && smem_bytes_for(sc, P.rb, P.h0_slots, 4) <= budget) ? 4 : 3;
-    const uint32_t smem = smem_bytes_for(sc, P.rb, P.h0_slots, P.nslot);
+    P.nslot = (sc != 0 && !split && P.rb <= 16448 && smem_bytes_for(sc, P.rb, P.h0_slots, 4) <= budget) ? 4 : 3;
+    const uint32_t smem = smem_bytes_for(sc, P.rb, P.h0_slots, P.nslot, split);
     KernelFn fn = pick_kernel((int)(g.bpp / 4), sc);
     cudaError_t e; // (the dynamic shared-memory limit was raised once per device by fast_tier_init)
     int occ = 0;

@@ -356,3 +356,42 @@ def test_argument_errors_are_reported():
     # empty image data: nothing to do, no rows
     ok = _lib.CStrategy(1, 0, None, 0)
     assert L.oxi_filter_image(C.byref(h), d.ctypes.data, 0, C.byref(ok), 0, out.ctypes.data, used.ctypes.data, None) == 0
+
+
+def test_split_table_bigram_rows_16k_to_32k():
+    """Bigrams / BigEnt on rows of 16 KB .. 32 KB (bigram_row_split: tables A[a<32][b] and B[a][b<32], outlier hash, coarse
+    trial 0 with exact recount, flagged trials recounted by bigram_trial): 16-bit images whose low bytes are noise, 8-bit
+    images, every filter bpp, ragged row lengths, Adam7, and contents that force each fallback."""
+    import oxipng_b200 as ox
+    rng = np.random.default_rng(1234)
+    shapes = [
+        (2100, 7, 6, 16, False, "photo"),     # 16 800-byte rows, bpp 8
+        (4096, 5, 6, 16, False, "photo"),     # 32 768-byte rows (the c3a shape)
+        (4095, 4, 2, 16, False, "photo"),     # bpp 6, 24 570-byte rows (not a multiple of 4)
+        (8000, 4, 4, 16, False, "photo"),     # bpp 4
+        (10000, 4, 0, 16, False, "photo"),    # bpp 2
+        (4200, 6, 6, 8, False, "photo"),      # 8-bit, bpp 4: everything lands in table A
+        (5467, 5, 2, 8, False, "photo"),      # bpp 3, 16 401-byte rows
+        (20001, 4, 0, 8, False, "photo"),     # bpp 1
+        (4096, 5, 6, 16, False, "random"),    # both residuals far from zero: outlier hash overflows, exact recounts
+        (4096, 4, 6, 16, False, "flat"),      # ties, None competitive
+        (4096, 4, 6, 16, False, "zeros"),     # all-zero shortcut
+        (4000, 40, 6, 16, True, "photo"),     # Adam7: passes with rows of 4 .. 32 KB in one launch
+    ]
+    for (w, h, ct, bd, il, kind) in shapes:
+        ih, d = helpers.synth_image(w, h, ct, bd, 777 + w, kind, il)
+        _check(ih, d, alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["Bigrams", "BigEnt"],
+               label=f"split/{w}x{h}/{ct}/{bd}/{il}/{kind}")
+        _check(ih, d, alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["None", "Bigrams", "BigEnt"],
+               label=f"split3/{w}x{h}/{ct}/{bd}/{il}/{kind}")
+    # rows where None wins or ties (exact trial 0), and rows with a few far-out windows (outlier hash without overflow)
+    w, h = 4096, 6
+    a = np.zeros((h, w * 8), np.uint8)
+    a[1] = np.tile(np.array([7, 9], np.uint8), w * 4)             # two bigrams only: None beats every filter
+    a[2] = a[1]
+    a[3] = rng.integers(0, 3, size=w * 8, dtype=np.uint8)         # tiny alphabet
+    a[4] = a[3]
+    a[4, rng.choice(w * 8, size=50, replace=False)] = 200          # 50 spikes: outlier windows in every trial
+    a[5] = a[4]
+    _check((w, h, 6, 16, 0), a.reshape(-1), alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["Bigrams", "BigEnt"],
+           label="split/none-wins")
