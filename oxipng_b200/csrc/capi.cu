@@ -285,6 +285,13 @@ int run_filters(DeviceCtx *c, Slot *slot, cudaStream_t stream, const Geom &g, co
         if (e != cudaSuccess) return fail_cuda(e, "launch_fast");
         return OXI_OK;
     }
+    if (g.alpha_bytes && !(flags & OXI_FLAG_FORCE_GENERIC) && alpha_supported(g, set)) {
+        lc.scratch = nullptr;
+        lc.scratch_bytes = 0;
+        e = launch_alpha(lc, g, d_data, n_images, set);
+        if (e != cudaSuccess) return fail_cuda(e, "launch_alpha");
+        return OXI_OK;
+    }
     if (flags & OXI_FLAG_FORCE_FAST) return fail(OXI_E_UNSUPPORTED, "fast tier does not cover this call");
     size_t need = generic_scratch_bytes(g, n_images, c->num_sms, nullptr);
     e = grow(&slot->scratch, &slot->scratch_bytes, need);
@@ -554,7 +561,8 @@ const char *oxi_filter_tier(const oxi_ihdr *h, size_t data_len, const oxi_strate
     set.k = 1;
     set.s[0].kind = st->kind;
     set.s[0].basic = st->basic_filter;
-    return fast_supported(g, set) ? "fast" : "generic"; // (a device whose shared-memory window differs runs generic)
+    if (fast_supported(g, set)) return "fast"; // (a device whose shared-memory window differs runs generic)
+    return alpha_supported(g, set) ? "alpha" : "generic";
 }
 
 int oxi_filter_batch_device(int device, void *stream, const oxi_ihdr *h, const uint8_t *d_data, size_t data_len,

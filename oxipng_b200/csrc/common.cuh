@@ -148,6 +148,11 @@ bool fast_tier_usable(uint32_t smem_window);
 cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_data, size_t n_images,
                         const StrategySet &set);
 
+// optimize_alpha tier (filter_fast.cu, k_alpha): rows serial per (image, strategy) chain, everything staged in shared memory
+bool alpha_supported(const Geom &g, const StrategySet &set);
+cudaError_t launch_alpha(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_data, size_t n_images,
+                         const StrategySet &set);
+
 void count_launch(uint64_t n = 1);
 
 } // namespace oxi

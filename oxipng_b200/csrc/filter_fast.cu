@@ -1184,7 +1184,7 @@ __device__ __noinline__ int decide_row(const DevStrategy &st, uint32_t r, uint32
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 template <int D, int SC>
-__global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (SC & SC_BIGRAM) ? 1 : (SC == SC_MINSUM || SC == 0) ? 3 : 2) k_fast(const __grid_constant__ FastParams P) {
+__global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? ((SC & SC_ENTROPY) ? HALF_OCC - 1 : HALF_OCC) : (SC & SC_BIGRAM) ? 1 : (SC == SC_MINSUM || SC == 0) ? 3 : 2) k_fast(const __grid_constant__ FastParams P) {
     constexpr int NT = threads_for(SC);
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t NS = P.nslot;
@@ -1405,6 +1405,334 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? HALF_OCC : (
     }
 }
 
+// ---- optimize_alpha tier (filters/mod.rs:114-186, png/mod.rs:363-367,412-423) -----------------------------------------------
+// With alpha optimisation every trial rewrites the colour bytes of fully transparent pixels so that they filter to zero,
+// the five trials mutate ONE line cumulatively, and the next row is filtered against the winning trial's rewritten line:
+// rows are serial, so the parallelism is across (image, strategy) chains and inside a row.  One 256-thread CTA walks a
+// chain with everything in shared memory: two ring slots that receive the rows by TMA and serve as the mutable line, two
+// buffers that alternate as "previous row as left by the winner" and "best line so far", and the scorer's table (one
+// 256-bin histogram x 4 replicas, or one hash table of whole-row bigrams).  Trials are scored on the fly from (line,
+// previous) with the byte-SIMD filters of the fast tier; the chosen row is written by the fast tier's write_row.
+constexpr int ALPHA_NT = 256;
+constexpr uint32_t ALPHA_HDR = 512;
+enum { AK_FIXED = 0, AK_MINSUM = 1, AK_ENTROPY = 2, AK_BIGRAM = 3 };
+
+struct AlphaParams {
+    Geom g;
+    StrategySet set;
+    const uint8_t *data;
+    uint64_t n_images;
+    uint32_t rb;       // bytes of one row buffer (PAD + row + PAD)
+    uint32_t hslots;   // AK_BIGRAM: slots of the hash table (power of two, > 2 * row bytes)
+    uint32_t n_sel;    // strategies handled by this launch
+    uint8_t sel[MAX_STRATEGIES];
+};
+
+__device__ __forceinline__ bool px_clear(const uint8_t *px, uint32_t cb, uint32_t bpp) { // alpha bytes all zero
+    for (uint32_t k = cb; k < bpp; k++)
+        if (px[k]) return false;
+    return true;
+}
+
+// RowFilter::optimize_alpha for one row held in shared memory, any pixel format.  Alpha bytes are never written, so
+// "transparent" is a fixed property of each pixel; every maximal run of transparent pixels is rewritten left to right by
+// the thread that finds its first pixel (runs are disjoint; a run reads only the opaque pixel before it, the previous row
+// and its own earlier writes).  RGBA8 (bpp 4, one pixel = one word) walks the runs with byte-SIMD word operations.
+__device__ __noinline__ void alpha_rewrite_row(int f, uint8_t *line, const uint8_t *prev, uint32_t len, uint32_t bpp, uint32_t cb,
+                                               uint32_t *sh_first) {
+    if (f == 0) return; // "Assume transparent pixels already set to 0"
+    const uint32_t npix = len / bpp;
+    const int tid = threadIdx.x;
+    const bool rgba8 = bpp == 4 && cb == 3;
+    uint32_t *lw = reinterpret_cast<uint32_t *>(line);
+    const uint32_t *pw = reinterpret_cast<const uint32_t *>(prev);
+    if (f == 2) { // Up: copy the colour bytes of the pixel above
+        if (rgba8) {
+            for (uint32_t i = tid; i < npix; i += ALPHA_NT)
+                if ((lw[i] >> 24) == 0) lw[i] = pw[i] & 0x00FFFFFFu;
+        } else {
+            for (uint32_t i = tid; i < npix; i += ALPHA_NT)
+                if (px_clear(line + (size_t)i * bpp, cb, bpp))
+                    for (uint32_t j = 0; j < cb; j++) line[(size_t)i * bpp + j] = prev[(size_t)i * bpp + j];
+        }
+        __syncthreads();
+        return;
+    }
+    // first non-transparent pixel (only matters when pixel 0 is transparent), mod.rs:126-131
+    if (tid == 0) *sh_first = 0xFFFFFFFFu;
+    __syncthreads();
+    if (npix && px_clear(line, cb, bpp)) {
+        uint32_t mine = 0xFFFFFFFFu;
+        for (uint32_t i = tid; i < npix; i += ALPHA_NT)
+            if (!px_clear(line + (size_t)i * bpp, cb, bpp)) { mine = i; break; }
+        if (mine != 0xFFFFFFFFu) atomicMin(sh_first, mine);
+    }
+    __syncthreads();
+    const uint32_t first_opaque = *sh_first; // 0xFFFFFFFF: none -> prev = i (= 0)
+    const uint32_t pv0 = first_opaque == 0xFFFFFFFFu ? 0u : first_opaque;
+    for (uint32_t s0 = tid; s0 < npix; s0 += ALPHA_NT) {
+        if (rgba8) {
+            if ((lw[s0] >> 24) != 0) continue;
+            if (s0 > 0 && (lw[s0 - 1] >> 24) == 0) continue; // not a run start
+            uint32_t left = s0 ? lw[s0 - 1] : 0u, ul = s0 ? pw[s0 - 1] : 0u;
+            for (uint32_t i = s0; i < npix; i++) {
+                if (i > s0 && (lw[i] >> 24) != 0) break;
+                const uint32_t up = pw[i];
+                uint32_t v;
+                if (f == 1) v = i == 0 ? lw[pv0] : left;                              // Sub: colour of the pixel before
+                else if (f == 3) v = i == 0 ? ((up >> 1) & 0x7F7F7F7Fu) : __vhaddu4(left, up); // Average
+                else v = i == 0 ? __vminu4(lw[pv0], up) : paeth4(left, up, ul);               // Paeth
+                v &= 0x00FFFFFFu;
+                lw[i] = v;
+                left = v;
+                ul = up;
+            }
+        } else {
+            uint8_t *px = line + (size_t)s0 * bpp;
+            if (!px_clear(px, cb, bpp)) continue;
+            if (s0 > 0 && px_clear(px - bpp, cb, bpp)) continue; // not a run start
+            for (uint32_t i = s0; i < npix; i++) {
+                px = line + (size_t)i * bpp;
+                if (i > s0 && !px_clear(px, cb, bpp)) break;
+                const uint8_t *up = prev + (size_t)i * bpp;
+                const uint32_t pv = i == 0 ? pv0 : i - 1;
+                for (uint32_t j = 0; j < cb; j++) {
+                    uint32_t v;
+                    if (f == 1) {
+                        v = line[(size_t)pv * bpp + j];
+                    } else if (f == 3) {
+                        v = i == 0 ? (uint32_t)(up[j] >> 1) : (((uint32_t)px[(int)j - (int)bpp] + up[j]) >> 1);
+                    } else if (i == 0) {
+                        const uint32_t a = line[(size_t)pv * bpp + j];
+                        v = a < up[j] ? a : up[j];
+                    } else {
+                        v = paeth(px[(int)j - (int)bpp], up[j], up[(int)j - (int)bpp]);
+                    }
+                    px[j] = (uint8_t)v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// residual words of one 16-byte chunk of the row under filter f (run time), bytes past the row masked to zero
+template <int D>
+__device__ __forceinline__ void alpha_residual_chunk(int f, const uint8_t *cur, const uint8_t *up, uint32_t c, int valid,
+                                                     uint32_t shift, uint32_t (&r)[4]) {
+    const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t x = cw.w[k + 2];
+        uint32_t pr = 0;
+        if (f == 1) pr = left_word<D>(cw, k, shift);
+        else if (f == 2) pr = uw.w[k + 2];
+        else if (f == 3) pr = __vhaddu4(left_word<D>(cw, k, shift), uw.w[k + 2]);
+        else if (f == 4) pr = paeth4(left_word<D>(cw, k, shift), uw.w[k + 2], left_word<D>(uw, k, shift));
+        r[k] = __vsub4(x, pr) & tail_mask(valid - 4 * k);
+    }
+}
+
+// Score of trial f of the line (cur, up) under scorer KIND; every thread returns the same value.
+// MinSum / Bigrams: lower is better; Entropy / BigEnt: higher is better as i32 (strategies.rs:95,143,189,221).
+template <int D, int KIND>
+__device__ __forceinline__ uint32_t alpha_score(int f, int kind, const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
+                                                uint32_t *tab, uint32_t hslots, uint32_t *acc /* [2], zero on entry */) {
+    const uint32_t nchunks = (len + 15) >> 4, lane = threadIdx.x & 31u;
+    if (KIND == AK_MINSUM) {
+        uint32_t a = 0; // sum over bytes of ||r| - 128| (see minsum_chunk); bytes past the row give 128 each
+        for (uint32_t c = threadIdx.x; c < nchunks; c += ALPHA_NT) {
+            uint32_t r[4];
+            alpha_residual_chunk<D>(f, cur, up, c, (int)len - 16 * (int)c, shift, r);
+#pragma unroll
+            for (int k = 0; k < 4; k++) a += __vsadu4(r[k], 0x80808080u); // |r as i8| = 128 - |r - 128|
+        }
+        a = warp_sum(a);
+        if (lane == 0 && a) atomicAdd(&acc[0], a);
+        __syncthreads();
+        const uint32_t sres = 128u * 16u * nchunks - acc[0] + (uint32_t)f; // + |f| of the filter-type byte
+        __syncthreads();
+        if (threadIdx.x == 0) acc[0] = 0;
+        return sres;
+    }
+    if (KIND == AK_ENTROPY) {
+        const uint32_t rep = threadIdx.x & 3u;
+        for (uint32_t c = threadIdx.x; c < nchunks; c += ALPHA_NT) {
+            uint32_t r[4];
+            const int valid = (int)len - 16 * (int)c;
+            alpha_residual_chunk<D>(f, cur, up, c, valid, shift, r);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                for (int j = 0; j < 4; j++)
+                    if (4 * k + j < valid) atomicAdd(&tab[rep * 256u + ((r[k] >> (8 * j)) & 255u)], 1u);
+        }
+        __syncthreads();
+        uint32_t e = 0;
+        {
+            const uint32_t v = threadIdx.x; // one bin per thread (ALPHA_NT == 256)
+            const uint32_t cnt = tab[v] + tab[256 + v] + tab[512 + v] + tab[768 + v] + (v == (uint32_t)f ? 1u : 0u);
+            tab[v] = tab[256 + v] = tab[512 + v] = tab[768 + v] = 0;
+            e = cnt ? ilog2i(cnt) : 0u;
+        }
+        e = warp_sum(e);
+        if (lane == 0 && e) atomicAdd(&acc[0], e);
+        __syncthreads();
+        const uint32_t sres = acc[0];
+        __syncthreads();
+        if (threadIdx.x == 0) acc[0] = 0;
+        return sres;
+    }
+    // AK_BIGRAM: every window (t[p-1], t[p]), p = 1..len, t[0] = f, into the hash table; distinct keys / sum ilog2i(count)
+    const uint32_t hmask = hslots - 1, hshift = (uint32_t)__clz((int)hslots) + 1;
+    for (uint32_t c = threadIdx.x; c < ((nchunks + 31u) & ~31u); c += ALPHA_NT) {
+        uint32_t r[4] = {0, 0, 0, 0};
+        const int valid = (int)len - 16 * (int)c;
+        if (c < nchunks) alpha_residual_chunk<D>(f, cur, up, c, valid, shift, r);
+        uint32_t p = __shfl_up_sync(0xffffffffu, r[3] >> 24, 1);
+        if (lane == 0) p = c == 0 ? (uint32_t)f : (c < nchunks ? residual_at(f, cur, up, 16 * (int)c - 1, (int)(D * 4 + shift / 8)) : 0u);
+        if (c >= nchunks) continue;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            for (int j = 0; j < 4; j++) {
+                const uint32_t b = (r[k] >> (8 * j)) & 255u;
+                if (4 * k + j < valid) h0_add(tab, (p << 8) | b, hshift, hmask);
+                p = b;
+            }
+    }
+    __syncthreads();
+    uint32_t d = 0, e = 0;
+    h0_sweep<ALPHA_NT>(tab, hslots, d, e);
+    d = warp_sum(d);
+    e = warp_sum(e);
+    if (lane == 0 && d) {
+        atomicAdd(&acc[0], d);
+        atomicAdd(&acc[1], e);
+    }
+    __syncthreads();
+    const uint32_t sres = kind == OXI_BIGRAMS ? acc[0] : acc[1];
+    __syncthreads();
+    if (threadIdx.x == 0) acc[0] = acc[1] = 0;
+    return sres;
+}
+
+template <int D, int KIND>
+__global__ void __launch_bounds__(ALPHA_NT, 4) k_alpha(const __grid_constant__ AlphaParams P) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);                 // 2 mbarriers
+    uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw + 64);            // [2] score accumulators
+    uint32_t *sh_first = reinterpret_cast<uint32_t *>(smem_raw + 80);
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw + ALPHA_HDR);
+    const uint32_t tab_bytes = KIND == AK_ENTROPY ? 4096u : KIND == AK_BIGRAM ? P.hslots * 4u : 0u;
+    uint8_t *bufs = smem_raw + ALPHA_HDR + tab_bytes; // ring slot 0, ring slot 1, keep A, keep B
+    const int tid = threadIdx.x;
+    const uint32_t bpp = P.g.bpp, cb = P.g.color_bytes, shift = 8 * (bpp % 4);
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        acc[0] = acc[1] = 0;
+    }
+    for (uint32_t i = tid; i < (tab_bytes + 4u * P.rb) / 4; i += ALPHA_NT) reinterpret_cast<uint32_t *>(smem_raw + ALPHA_HDR)[i] = 0;
+    __syncthreads();
+    uint32_t parity = 0;
+    const uint64_t items = (uint64_t)P.n_sel * P.n_images;
+    for (uint64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const DevStrategy &st = P.set.s[P.sel[it / P.n_images]];
+        const uint64_t img = it % P.n_images;
+        const uint8_t *in = P.data + img * P.g.data_len;
+        for (uint32_t p = 0; p < P.g.n_pass; p++) {
+            const PassDesc pd = P.g.pass[p];
+            const uint32_t len = pd.len;
+            const uint8_t *src0 = in + pd.in_base;
+            const bool tma = ((reinterpret_cast<uintptr_t>(src0) | len) & 15u) == 0;
+            uint8_t *keep_prev = bufs + 2 * (size_t)P.rb + PAD, *keep_best = bufs + 3 * (size_t)P.rb + PAD;
+            // previous row of a pass's first row: zeros (png/mod.rs:375-378); also re-zero the tails of the ring slots
+            // (a longer row of an earlier pass may have left bytes behind this pass's row length)
+            for (uint32_t b = 0; b < 4; b++) {
+                uint4 *z = reinterpret_cast<uint4 *>(bufs + b * (size_t)P.rb + PAD);
+                for (uint32_t i = tid; i < (P.rb - 2 * PAD) / 16; i += ALPHA_NT) z[i] = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async();
+            __syncthreads();
+            // first row of the pass into ring slot 0
+            if (tma) {
+                if (tid == 0) {
+                    mbar_expect_tx(&bar[0], len);
+                    tma_load_1d(bufs + PAD, src0, len, &bar[0]);
+                }
+            } else {
+                coop_load_row<ALPHA_NT>(bufs + PAD, src0, len);
+            }
+            for (uint32_t k = 0; k < pd.nrows; k++) {
+                const uint32_t slot = k & 1u;
+                uint8_t *w = bufs + slot * (size_t)P.rb + PAD;
+                // the next row streams into the other slot (its last reader was row k-1, behind that row's final barrier)
+                if (k + 1 < pd.nrows) {
+                    uint8_t *nxt = bufs + (slot ^ 1u) * (size_t)P.rb + PAD;
+                    if (tma) {
+                        if (tid == 0) {
+                            mbar_expect_tx(&bar[slot ^ 1u], len);
+                            tma_load_1d(nxt, src0 + (size_t)(k + 1) * len, len, &bar[slot ^ 1u]);
+                        }
+                    } else {
+                        coop_load_row<ALPHA_NT>(nxt, src0 + (size_t)(k + 1) * len, len);
+                    }
+                }
+                if (tma) {
+                    mbar_wait(&bar[slot], (parity >> slot) & 1u);
+                    parity ^= 1u << slot;
+                } else {
+                    __syncthreads();
+                }
+                const uint32_t r = pd.row0 + k;
+                uint8_t *out_row = st.out + img * P.g.out_len + pd.in_base + r + (uint64_t)k * len;
+                int best_f = 0;
+                const uint8_t *final_line = w;
+                if (KIND == AK_FIXED) { // Basic / Predefined (png/mod.rs:382-394)
+                    best_f = st.kind == OXI_BASIC ? st.basic : (r < st.n_predefined ? st.predefined[r] : 0);
+                    alpha_rewrite_row(best_f, w, keep_prev, len, bpp, cb, sh_first);
+                } else {
+                    // all-zero rows short-circuit to None (png/mod.rs:398-404)
+                    uint32_t nz = 0;
+                    const uint4 *c4 = reinterpret_cast<const uint4 *>(w);
+                    for (uint32_t c = tid; c < (len + 15) / 16; c += ALPHA_NT) { const uint4 v = c4[c]; nz |= v.x | v.y | v.z | v.w; }
+                    if (__syncthreads_or(nz != 0)) {
+                        uint32_t best = 0;
+                        for (int f = 0; f < 5; f++) { // RowFilter::ALL order, cumulative rewriting of the one line
+                            alpha_rewrite_row(f, w, keep_prev, len, bpp, cb, sh_first);
+                            const uint32_t sres = alpha_score<D, KIND>(f, st.kind, w, keep_prev, len, shift, tab, P.hslots, acc);
+                            const bool lower = st.kind == OXI_MINSUM || st.kind == OXI_BIGRAMS;
+                            if (f == 0 || (lower ? sres < best : (int32_t)sres > (int32_t)best)) {
+                                best = sres;
+                                best_f = f;
+                                if (f < 4) { // keep the line as this trial left it (the last trial's line is `w` itself)
+                                    const uint4 *s4 = reinterpret_cast<const uint4 *>(w);
+                                    uint4 *d4 = reinterpret_cast<uint4 *>(keep_best);
+                                    for (uint32_t c = tid; c < (len + 15) / 16; c += ALPHA_NT) d4[c] = s4[c];
+                                }
+                            }
+                        }
+                        __syncthreads();
+                        final_line = best_f == 4 ? w : keep_best;
+                    }
+                }
+                // write the chosen row from (its rewritten line, previous line); then it becomes the previous line
+                write_row<ALPHA_NT, false>(best_f, final_line, keep_prev, len, (int)bpp, out_row);
+                if (tid == 0) st.filters_used[img * P.g.total_rows + r] = (uint8_t)best_f;
+                __syncthreads();
+                if (final_line == keep_best) { // swap the keep buffers
+                    uint8_t *t = keep_prev; keep_prev = keep_best; keep_best = t;
+                } else { // the line lives in a ring slot that the next-but-one row will overwrite: copy it
+                    const uint4 *s4 = reinterpret_cast<const uint4 *>(final_line);
+                    uint4 *d4 = reinterpret_cast<uint4 *>(keep_prev);
+                    for (uint32_t c = tid; c < (len + 15) / 16; c += ALPHA_NT) d4[c] = s4[c];
+                    __syncthreads();
+                }
+            }
+        }
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
 
 int scorers_needed(const StrategySet &set) {
@@ -1420,8 +1748,9 @@ int scorers_needed(const StrategySet &set) {
     return sc;
 }
 // Kernels are instantiated for the scorer sets that occur in practice; any other mixture runs the full kernel.
+// (Entropy + bigrams is the reference's default trial set {None, Sub, Entropy, Bigrams}, options.rs:282-287)
 int kernel_sc(int sc) {
-    if (sc == 0 || sc == SC_MINSUM || sc == SC_ENTROPY || sc == SC_BIGRAM) return sc;
+    if (sc == 0 || sc == SC_MINSUM || sc == SC_ENTROPY || sc == SC_BIGRAM || sc == (SC_ENTROPY | SC_BIGRAM)) return sc;
     return SC_MINSUM | SC_ENTROPY | SC_BIGRAM;
 }
 uint32_t slot_bytes(const Geom &g) { return PAD + ((g.max_len + 15u) & ~15u) + PAD; }
@@ -1435,10 +1764,41 @@ KernelFn pick_sc(int sc) {
     case SC_ENTROPY: return k_fast<D, SC_ENTROPY>;
     case SC_BIGRAM: return k_fast<D, SC_BIGRAM>;
     case SC_BIGRAM | SC_HALF: return k_fast<D, SC_BIGRAM | SC_HALF>;
+    case SC_ENTROPY | SC_BIGRAM: return k_fast<D, SC_ENTROPY | SC_BIGRAM>;
+    case SC_ENTROPY | SC_BIGRAM | SC_HALF: return k_fast<D, SC_ENTROPY | SC_BIGRAM | SC_HALF>;
     default: return k_fast<D, SC_MINSUM | SC_ENTROPY | SC_BIGRAM>;
     }
 }
 KernelFn pick_kernel(int d, int sc) { return d == 0 ? pick_sc<0>(sc) : d == 1 ? pick_sc<1>(sc) : pick_sc<2>(sc); }
+
+
+using AlphaFn = void (*)(const AlphaParams);
+template <int D>
+AlphaFn pick_alpha_kind(int kind) {
+    switch (kind) {
+    case AK_MINSUM: return k_alpha<D, AK_MINSUM>;
+    case AK_ENTROPY: return k_alpha<D, AK_ENTROPY>;
+    case AK_BIGRAM: return k_alpha<D, AK_BIGRAM>;
+    default: return k_alpha<D, AK_FIXED>;
+    }
+}
+AlphaFn pick_alpha(int d, int kind) { return d == 0 ? pick_alpha_kind<0>(kind) : d == 1 ? pick_alpha_kind<1>(kind) : pick_alpha_kind<2>(kind); }
+int alpha_kind_of(int strategy_kind) {
+    switch (strategy_kind) {
+    case OXI_MINSUM: return AK_MINSUM;
+    case OXI_ENTROPY: return AK_ENTROPY;
+    case OXI_BIGRAMS: case OXI_BIGENT: return AK_BIGRAM;
+    default: return AK_FIXED;
+    }
+}
+uint32_t alpha_hslots(const Geom &g) {
+    uint32_t h = 1024;
+    while (h < 2 * g.max_len) h *= 2;
+    return h;
+}
+uint32_t alpha_smem(const Geom &g, int kind) {
+    return ALPHA_HDR + (kind == AK_ENTROPY ? 4096u : kind == AK_BIGRAM ? alpha_hslots(g) * 4u : 0u) + 4u * slot_bytes(g);
+}
 
 std::mutex g_occ_mu;
 std::map<std::pair<const void *, uint32_t>, int> g_occ; // (kernel, smem) -> resident CTAs per SM
@@ -1453,11 +1813,17 @@ __global__ void k_probe_smem_window(uint32_t *out) {
 cudaError_t fast_tier_init(int device, uint32_t *smem_window) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
-    const int scs[6] = {0, SC_MINSUM, SC_ENTROPY, SC_BIGRAM, SC_BIGRAM | SC_HALF, SC_MINSUM | SC_ENTROPY | SC_BIGRAM};
+    const int scs[8] = {0, SC_MINSUM, SC_ENTROPY, SC_BIGRAM, SC_BIGRAM | SC_HALF, SC_ENTROPY | SC_BIGRAM,
+                        SC_ENTROPY | SC_BIGRAM | SC_HALF, SC_MINSUM | SC_ENTROPY | SC_BIGRAM};
     for (int d = 0; d < 3; d++)
-        for (int i = 0; i < 6; i++) {
+        for (int i = 0; i < 8; i++) {
             e = cudaFuncSetAttribute((const void *)pick_kernel(d, scs[i]), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)SMEM_LIMIT);
+            if (e != cudaSuccess) return e;
+        }
+    for (int d = 0; d < 3; d++)
+        for (int kind = AK_FIXED; kind <= AK_BIGRAM; kind++) {
+            e = cudaFuncSetAttribute((const void *)pick_alpha(d, kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
             if (e != cudaSuccess) return e;
         }
     uint32_t *d_w = nullptr, w = 0;
@@ -1470,6 +1836,48 @@ cudaError_t fast_tier_init(int device, uint32_t *smem_window) {
     *smem_window = w;
     return cudaSuccess;
 }
+// optimize_alpha tier: images with an alpha channel whose rows (four staged copies + the scorer's table) fit shared memory
+bool alpha_supported(const Geom &g, const StrategySet &set) {
+    if (g.alpha_bytes == 0 || g.total_rows == 0) return false;
+    if (g.bpp != 2 && g.bpp != 4 && g.bpp != 8) return false; // GA8, GA16 / RGBA8, RGBA16
+    for (int j = 0; j < set.k; j++) {
+        const int kind = alpha_kind_of(set.s[j].kind);
+        if (alpha_smem(g, kind) > SMEM_LIMIT) return false;
+        if (kind == AK_BIGRAM && g.max_len > 16384u) return false; // 15-bit counts in the hash entries
+    }
+    return true;
+}
+
+cudaError_t launch_alpha(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_data, size_t n_images, const StrategySet &set) {
+    for (int kind = AK_FIXED; kind <= AK_BIGRAM; kind++) {
+        AlphaParams P;
+        P.g = g;
+        P.set = set;
+        P.data = d_data;
+        P.n_images = n_images;
+        P.rb = slot_bytes(g);
+        P.hslots = alpha_hslots(g);
+        P.n_sel = 0;
+        for (int j = 0; j < set.k; j++)
+            if (alpha_kind_of(set.s[j].kind) == kind) P.sel[P.n_sel++] = (uint8_t)j;
+        if (P.n_sel == 0) continue;
+        const uint32_t smem = alpha_smem(g, kind);
+        AlphaFn fn = pick_alpha((int)(g.bpp / 4), kind);
+        int occ = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, ALPHA_NT, smem);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+        const uint64_t items = (uint64_t)P.n_sel * n_images;
+        uint64_t grid = (uint64_t)ctx.num_sms * occ;
+        if (grid > items) grid = items;
+        fn<<<(unsigned)grid, ALPHA_NT, smem, ctx.stream>>>(P);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 // the bigram and Entropy scorers address their tables as [register + immediate] from SMEM_WIN
 bool fast_tier_usable(uint32_t smem_window) { return smem_window == SMEM_WIN; }
 
@@ -1502,8 +1910,12 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
     if (split) P.small_tab = 2;
     // ... and with rows <= 4096 bytes two 512-thread CTAs fit an SM (two rows in flight: one CTA's barriers and table
     // sweeps overlap the other's counting)
-    const uint32_t two_per_sm = (233472u / HALF_OCC - 1024u) & ~127u; // shared memory of one of HALF_OCC resident CTAs
-    if (sc == SC_BIGRAM && P.small_tab && g.max_len <= 4096 && smem_bytes_for(sc | SC_HALF, P.rb, h0, 3) <= two_per_sm) sc |= SC_HALF;
+    // (with the Entropy histograms resident as well: three CTAs per SM)
+    const uint32_t half_occ = (sc & SC_ENTROPY) ? HALF_OCC - 1 : HALF_OCC;
+    const uint32_t two_per_sm = (233472u / half_occ - 1024u) & ~127u; // shared memory of one of half_occ resident CTAs
+    if ((sc == SC_BIGRAM || sc == (SC_ENTROPY | SC_BIGRAM)) && P.small_tab && g.max_len <= 4096 &&
+        smem_bytes_for(sc | SC_HALF, P.rb, h0, 3) <= two_per_sm)
+        sc |= SC_HALF;
     const int nt = threads_for(sc);
     // a fourth ring slot removes the end-of-row barrier; take it when it does not cost occupancy (rows <= 16 KB)
     const uint32_t budget = (sc & SC_HALF) ? two_per_sm : SMEM_LIMIT;

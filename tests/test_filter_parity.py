@@ -395,3 +395,16 @@ def test_split_table_bigram_rows_16k_to_32k():
     a[5] = a[4]
     _check((w, h, 6, 16, 0), a.reshape(-1), alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["Bigrams", "BigEnt"],
            label="split/none-wins")
+
+
+def test_default_trial_set_entropy_plus_bigrams_kernel():
+    """The reference's default set {None, Sub, Entropy, Bigrams} (options.rs:282-287) runs in its own kernels
+    (k_fast<D, SC_ENTROPY|SC_BIGRAM[|SC_HALF]>): short rows (256-thread CTAs), long rows, every bpp class, odd lengths."""
+    import oxipng_b200 as ox
+    for (w, h, ct, bd, il, kind) in [(1024, 9, 6, 8, False, "photo"), (300, 12, 2, 8, False, "photo"), (333, 7, 6, 16, False, "photo"),
+                                     (1000, 6, 0, 8, False, "random"), (256, 20, 6, 8, False, "flat"), (256, 8, 6, 8, False, "zeros"),
+                                     (3000, 5, 6, 8, False, "photo"), (777, 40, 6, 8, True, "photo"), (999, 9, 0, 4, False, "random")]:
+        ih, d = helpers.synth_image(w, h, ct, bd, 31 + w, kind, il)
+        _check(ih, d, alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["None", "Sub", "Entropy", "Bigrams"],
+               label=f"o2/{w}x{h}/{ct}/{bd}/{il}/{kind}")
+        _check(ih, d, alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["Entropy", "BigEnt"], label="E+BE")
