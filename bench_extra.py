@@ -163,9 +163,9 @@ def batch_configs(ox, synth, torch, dev, local, stream, peak, iters, n_images=25
         ("evaluator_set_none_bigrams_1024", base, [S.NONE, S.Bigrams], False, n_images),
         ("c5_noise6_none_bigrams_bigent_1024", noisy(6), [S.NONE, S.Bigrams, S.BigEnt], False, n_images),
         ("c5_noise12_none_bigrams_bigent_1024", noisy(12), [S.NONE, S.Bigrams, S.BigEnt], False, n_images),
-        ("alpha_optimize_minsum_rgba8_1024_10pct_transparent", transparent(), [S.MinSum], True, min(n_images, 128)),
+        ("alpha_optimize_minsum_rgba8_1024_10pct_transparent", transparent(), [S.MinSum], True, n_images),
         ("alpha_optimize_o2_set_rgba8_1024_10pct_transparent", None, [S.NONE, S.SUB, S.Entropy, S.Bigrams], True,
-         min(n_images, 128)),
+         n_images),
     ]
     last_alpha = None
     for name, d, strat, alpha, n in cfgs:

@@ -33,6 +33,9 @@ cfgs = {
     "c3b": (4096, 4096, 4, 8, [S.Bigrams, S.BigEnt], 1, True, 0),
     "c1bg": (4096, 4096, 4, 8, [S.Bigrams, S.BigEnt], 1, False, 0),
     "rgb8bg": (1365, 1024, 3, 8, [S.Bigrams, S.BigEnt], 64, False, 0),
+    # optimize_alpha on: 10 % of the 16x16 blocks fully transparent with random colour behind
+    "alpha_ms": (1024, 1024, 4, 8, [S.MinSum], 128, False, -2),
+    "alpha_o2": (1024, 1024, 4, 8, [S.NONE, S.SUB, S.Entropy, S.Bigrams], 128, False, -2),
 }
 out = {}
 for name in NAMES:
@@ -41,7 +44,15 @@ for name in NAMES:
     hdr = ox.IhdrData(w, h, ct, ox.BitDepth(bd), interlaced)
     per = w * h * ch * (bd // 8)
     d = synth.photo_batch(n, w, h, ch, bd, 0xB2000001, dev)
-    if noise < 0:
+    alpha = noise == -2
+    if alpha:
+        g = torch.Generator(device=dev); g.manual_seed(9)
+        v = d.view(n, h, w, 4)
+        m = (torch.rand((n, h // 16, w // 16), device=dev, generator=g) < 0.10).repeat_interleave(16, 1).repeat_interleave(16, 2)
+        rnd = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=dev, generator=g)
+        v[..., :3] = torch.where(m[..., None], rnd, v[..., :3])
+        v[..., 3] = torch.where(m, torch.zeros_like(v[..., 3]), v[..., 3])
+    elif noise < 0:
         g = torch.Generator(device=dev); g.manual_seed(7)
         d = torch.randint(0, 256, d.shape, dtype=torch.uint8, device=dev, generator=g)
     elif noise > 0:
@@ -63,7 +74,7 @@ for name in NAMES:
         flush.fill_(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
-        ox.filter_batch_device(0, st.cuda_stream, hdr, d.data_ptr(), per, n, strat, False, [t.data_ptr() for t in o],
+        ox.filter_batch_device(0, st.cuda_stream, hdr, d.data_ptr(), per, n, strat, alpha, [t.data_ptr() for t in o],
                                [t.data_ptr() for t in u])
         e1.record(st)
         torch.cuda.synchronize()

@@ -408,3 +408,54 @@ def test_default_trial_set_entropy_plus_bigrams_kernel():
         _check(ih, d, alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["None", "Sub", "Entropy", "Bigrams"],
                label=f"o2/{w}x{h}/{ct}/{bd}/{il}/{kind}")
         _check(ih, d, alphas=(False,), flags=ox.FLAG_FORCE_FAST, strategies=["Entropy", "BigEnt"], label="E+BE")
+
+
+def test_alpha_tier_staged_rows():
+    """optimize_alpha through the shared-memory tier (k_alpha): every alpha pixel format, rows up to 16 KB, Adam7, runs of
+    transparent pixels of every length (the run walkers), first pixel transparent, rows that are transparent throughout
+    with colour left behind (the cumulative-rewrite leak, filters/mod.rs:126-131), all-zero rows, all nine strategies."""
+    import oxipng_b200 as ox
+    rng = np.random.default_rng(99)
+    for (w, h, ct, bd, il) in [(64, 40, 6, 8, False), (300, 33, 6, 8, False), (1024, 12, 6, 8, False), (4000, 5, 6, 8, False),
+                               (257, 21, 4, 8, False), (190, 17, 6, 16, False), (333, 9, 4, 16, False), (131, 37, 6, 8, True),
+                               (90, 30, 4, 16, True), (2048, 6, 6, 16, False)]:
+        ih, d = helpers.synth_image(w, h, ct, bd, 4000 + w, "transparent", il)
+        img = helpers.product_image(ih, d)
+        assert ox.filter_tier(img, ox.FilterStrategy.MinSum, True) == "alpha", (w, h, ct, bd)
+        _check(ih, d, alphas=(True,), label=f"alpha/{w}x{h}/{ct}/{bd}/{il}")
+    # hand-built RGBA8 rows: long runs, leading / trailing runs, fully transparent rows with colour, alternate pixels
+    w, h = 600, 14
+    a = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+    a[..., 3] = 255
+    a[1, :400, 3] = 0                 # leading run of 400
+    a[2, 100:, 3] = 0                 # trailing run
+    a[3, :, 3] = 0                    # whole row transparent, colours random (nothing to copy from: prev == i)
+    a[4, :, 3] = 0
+    a[4, :, :3] = 0                   # whole row zero: None shortcut
+    a[5, ::2, 3] = 0                  # alternate pixels
+    a[6, 1::2, 3] = 0
+    a[7, 5:595, 3] = 0                # one long interior run
+    a[8, :, 3] = 0                    # transparent row after a long run row
+    a[9, :3, 3] = 0
+    a[10, 0, 3] = 0
+    a[11, -1, 3] = 0
+    a[12, :, 3] = (rng.random(w) < 0.5) * 255
+    _check((w, h, 6, 8, 0), a.reshape(-1), alphas=(True,), label="alpha/handmade")
+    pre = [(i * 3) % 5 for i in range(h)]
+    img = helpers.product_image((w, h, 6, 8, 0), a.reshape(-1))
+    want, _, _ = oracle.filter_image((w, h, 6, 8, 0), a.reshape(-1), oracle.PREDEFINED, 0, np.array(pre, np.uint8), True)
+    assert np.array_equal(img.filter_image(ox.FilterStrategy.Predefined(pre), True)[0], want)
+    # a batch: chains of different images and strategies run side by side
+    n = 9
+    imgs = [helpers.synth_image(200, 25, 6, 8, 700 + i, "transparent")[1] for i in range(n)]
+    hdr = helpers.product_image((200, 25, 6, 8, 0), imgs[0]).ihdr
+    S = ox.FilterStrategy
+    strat = [S.NONE, S.SUB, S.Entropy, S.Bigrams, S.MinSum, S.BigEnt]
+    outs, used = ox.filter_batch(hdr, np.concatenate(imgs), n, strat, True)
+    per = imgs[0].size + 25
+    kinds = [(oracle.BASIC, 0), (oracle.BASIC, 1), (oracle.ENTROPY, 0), (oracle.BIGRAMS, 0), (oracle.MINSUM, 0), (oracle.BIGENT, 0)]
+    for i in range(n):
+        for j, (k, b) in enumerate(kinds):
+            wnt, wu, _ = oracle.filter_image((200, 25, 6, 8, 0), imgs[i], k, b, None, True)
+            assert np.array_equal(outs[j][i * per:(i + 1) * per], wnt), (i, j)
+            assert np.array_equal(used[j][i * 25:(i + 1) * 25], wu), (i, j)
