@@ -32,6 +32,10 @@ namespace {
 constexpr int SC_MINSUM = 1, SC_ENTROPY = 2, SC_BIGRAM = 4;
 constexpr int SC_HALF = 8; // with SC_BIGRAM alone, rows <= 4096 bytes: 256-thread CTAs, four resident per SM
 constexpr int HALF_NT = 256, HALF_OCC = 4;
+// with SC_BIGRAM | SC_HALF: dense tables of 64 x 64 counters per trial (residuals in [-32, 31]) for images whose filtered rows
+// are spread wider than +-16 (film grain, dithering): 512-thread CTAs, two resident per SM
+constexpr int SC_WIDE = 16;
+__host__ __device__ constexpr int rb_of(int sc) { return (sc & SC_WIDE) ? 6 : 5; } // bits of a range code
 constexpr int HIST_REP = 4;      // copies of each Entropy histogram (lane & 3) to thin same-address atomics
 constexpr uint32_t PAD = 32;     // zero bytes in front of every staged row (left/upleft of the first pixel)
 constexpr uint32_t SMEM_HDR = 1024;
@@ -51,10 +55,12 @@ struct FastParams {
     uint32_t shift; // 8 * (bpp % 4): funnel-shift amount that turns a row word into its "left" word
     uint32_t nslot;     // ring slots (4 when shared memory allows: removes the end-of-row barrier; else 3)
     uint32_t h0_slots;  // bigram scorer with small_tab: slots of the trial-0 hash table (power of two, > 2 * row bytes)
+    const uint8_t *img_class; // optional per-image class written by k_spread_probe (0: residuals within +-16, 1: wider)
+    uint32_t want_class;      // the class this launch takes
     uint32_t small_tab; // bigram scorer: 1 = the dense-table layout (rows <= 16384 bytes), 2 = the split-table layout (<= 32768)
 };
 
-__host__ __device__ constexpr int threads_for(int sc) { return (sc & SC_HALF) ? HALF_NT : (sc & SC_BIGRAM) ? 1024 : sc == SC_ENTROPY ? 512 : 256; }
+__host__ __device__ constexpr int threads_for(int sc) { return (sc & SC_WIDE) ? 512 : (sc & SC_HALF) ? HALF_NT : (sc & SC_BIGRAM) ? 1024 : sc == SC_ENTROPY ? 512 : 256; }
 
 // ---- PTX wrappers: mbarrier + 1-D bulk tensor-memory-accelerator copy -----------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -195,7 +201,19 @@ __device__ __forceinline__ uint32_t residual_at(int f, const uint8_t *cur, const
 __device__ __forceinline__ uint32_t big_word(uint32_t bg) { return (bg >> 1) ^ ((bg >> 8) & 31u); }
 // dense tables: 32x32 keys as u32 counters, 2 lane-selected replicas each.  Trials 1..4: both bytes in [-16,15];
 // trial 0: the low five bits of both raw bytes (a coarsening that bounds the trial's scores, see bigram_row_small)
-constexpr uint32_t DENSE_WORDS = 4 * 2 * 1024 + 1024; // trials 1..4 (two replicas each), then the coarse table of trial 0
+// Geometry of the dense-table region for range codes of RB bits (code = residual + 2^(RB-1)): the four trial tables, the
+// coarse table of trial 0 (8 KB, every other 128-byte line used), then the outlier hashes.  With RB = 5 the region is kept
+// at 36 KB so that the hash of whole rows (h0, 32 KB for 4 KB rows) can live in it while the tables are idle.
+template <int RB>
+struct Dense {
+    static constexpr uint32_t HALF = 1u << (RB - 1);
+    static constexpr uint32_t OUT = RB == 5 ? 0xE0u : 0xC0u;       // bits that are set in a code outside the range
+    static constexpr uint32_t OUT4 = OUT * 0x01010101u;
+    static constexpr uint32_t TABLES = 16u << (2 * RB);            // bytes of the four trial tables: 16 KB / 64 KB
+    static constexpr uint32_t COARSE = TABLES;                     // byte offset of the coarse table
+    static constexpr uint32_t REGION = RB == 5 ? 36864u : TABLES + 8192u;
+    static constexpr uint32_t SMALL = REGION + 4 * HSLOTS * 4;     // ... + outlier hashes
+};
 
 // ---- shared-memory carve-up --------------------------------------------------------------------------------------
 struct Smem {
@@ -212,7 +230,6 @@ struct Smem {
     uint32_t *small;   // DENSE_WORDS counters of the in-range bigrams of trials 1..4 (layout: dense_off), optional
     uint32_t *ohash;   // [4][HSLOTS] outlier bigrams of trials 1..4: open-addressing tables of (key << 16 | count)
 };
-constexpr uint32_t SMALL_BYTES = DENSE_WORDS * 4 + 4 * HSLOTS * 4; // dense tables + outlier hashes
 // h0_slots != 0 selects the small-table layout: header | histograms | dense tables | outlier hashes | h0 | row ring.
 // The tables come first so that their shared-memory offsets are compile-time constants (immediates of the atomics).
 // Otherwise: header | histograms | row ring | 65536-entry bigram table.
@@ -237,9 +254,9 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot
     s.hist = reinterpret_cast<uint32_t *>(p); // histograms first: fixed offset, immediates of the atomics
     if (SC & SC_ENTROPY) p += 5 * HIST_REP * 256 * 4;
     s.small = reinterpret_cast<uint32_t *>(p);
-    s.ohash = s.small + DENSE_WORDS;
+    s.ohash = s.small + Dense<rb_of(SC)>::REGION / 4;
     s.table = s.ohash + 4 * HSLOTS;
-    if ((SC & SC_BIGRAM) && h0_slots) p += SMALL_BYTES + ((SC & SC_HALF) ? 0u : h0_slots * 4);
+    if ((SC & SC_BIGRAM) && h0_slots) p += Dense<rb_of(SC)>::SMALL + ((SC & SC_HALF) ? 0u : h0_slots * 4);
     // SC_HALF: h0 (<= 8192 slots) is only used while the dense tables are swept clean and idle (exact pass of trial 0,
     // flagged outliers) and leaves them clean: it lives in their memory
     if (SC & SC_HALF) s.table = s.small;
@@ -253,7 +270,8 @@ __host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, uint32_t h0_slots, 
     if (split) return SMEM_HDR + SPLIT_BYTES + nslot * rb;
     uint32_t b = SMEM_HDR + nslot * rb;
     if (sc & SC_ENTROPY) b += 5 * HIST_REP * 256 * 4;
-    if (sc & SC_BIGRAM) b += h0_slots ? ((sc & SC_HALF) ? 0u : h0_slots * 4) + SMALL_BYTES : 65536 * 2;
+    if (sc & SC_BIGRAM)
+        b += h0_slots ? ((sc & SC_HALF) ? 0u : h0_slots * 4) + ((sc & SC_WIDE) ? Dense<6>::SMALL : Dense<5>::SMALL) : 65536 * 2;
     return b;
 }
 
@@ -574,40 +592,55 @@ __device__ __forceinline__ uint32_t ilog2i_z(uint32_t i) {
 // Lane-selected replicas and a per-lane rotation of the windows were measured in round 1 at 3.1 wavefronts per ATOMS;
 // replaying the kernel's lane -> window map on the bench images (profiles/r02_bank_sim.py) gives 3.06 for that layout
 // and 1.85 for this one, because the lanes of one instruction then count the same channel pair and mostly coincide.
-constexpr uint32_t COARSE_OFF = 16384; // byte offset of the coarse table of trial 0 behind the dense tables
+// RB = 6 (64 x 64 counters per trial): offset first << 10 | (f-1) << 8 | ((second + 3 * first) & 63) << 2; its high byte
+// (first << 2 | f-1) uses all eight bits, so it is stored with bit 7 inverted and the instruction's immediate carries
+// + 0x8000: prmt's sign replication then yields offset - 0x8000.
+template <int RB>
 __device__ __forceinline__ uint32_t dense_off(uint32_t f, uint32_t first, uint32_t second) {
-    return (first << 9) | ((f - 1u) << 7) | (((second + 5u * first) & 31u) << 2);
+    if (RB == 5) return (first << 9) | ((f - 1u) << 7) | (((second + 5u * first) & 31u) << 2);
+    return (first << 10) | ((f - 1u) << 8) | (((second + 3u * first) & 63u) << 2);
 }
 
 // One complete row word (four windows) of trial F.  t = range codes of the word's residual bytes, tpw = codes of the
-// stream bytes in front of them; all eight codes < 32.  DB = shared-window address of the dense tables.
-template <int F, uint32_t DB>
+// stream bytes in front of them; all eight codes in range.  DB = shared-window address of the dense tables.
+template <int F, uint32_t DB, int RB>
 __device__ __forceinline__ void dense_word(uint32_t t, uint32_t tpw) {
-    const uint32_t hi = tpw * 2u + (uint32_t)((F - 1) >> 1) * 0x01010101u;
-    const uint32_t s = tpw * 5u + t; // bytes <= 31 + 155: no carry between bytes; << 2 moves only bits the mask drops
-    const uint32_t lo = ((s << 2) & 0x7C7C7C7Cu) | ((uint32_t)((F - 1) & 1) * 0x80808080u);
-    smem_inc_at<DB>(prmt(lo, hi, 0xCC40u));
-    smem_inc_at<DB>(prmt(lo, hi, 0xDD51u));
-    smem_inc_at<DB>(prmt(lo, hi, 0xEE62u));
-    smem_inc_at<DB>(prmt(lo, hi, 0xFF73u));
+    if (RB == 5) {
+        const uint32_t hi = tpw * 2u + (uint32_t)((F - 1) >> 1) * 0x01010101u;
+        const uint32_t s = tpw * 5u + t; // bytes <= 31 + 155: no carry between bytes; << 2 moves only bits the mask drops
+        const uint32_t lo = ((s << 2) & 0x7C7C7C7Cu) | ((uint32_t)((F - 1) & 1) * 0x80808080u);
+        smem_inc_at<DB>(prmt(lo, hi, 0xCC40u));
+        smem_inc_at<DB>(prmt(lo, hi, 0xDD51u));
+        smem_inc_at<DB>(prmt(lo, hi, 0xEE62u));
+        smem_inc_at<DB>(prmt(lo, hi, 0xFF73u));
+    } else {
+        const uint32_t hi = (tpw * 4u + (uint32_t)(F - 1) * 0x01010101u) ^ 0x80808080u; // bytes <= 252 + 3
+        const uint32_t s = tpw * 3u + t;                                                 // bytes <= 189 + 63
+        const uint32_t lo = (s << 2) & 0xFCFCFCFCu;
+        smem_inc_at<DB + 0x8000u>(prmt(lo, hi, 0xCC40u));
+        smem_inc_at<DB + 0x8000u>(prmt(lo, hi, 0xDD51u));
+        smem_inc_at<DB + 0x8000u>(prmt(lo, hi, 0xEE62u));
+        smem_inc_at<DB + 0x8000u>(prmt(lo, hi, 0xFF73u));
+    }
 }
 // the same word window by window: tail words and words with an out-of-range byte
 // (one copy for all trials, F at run time: this path is off the straight line and should stay small in the i-cache;
 // it takes shared-window addresses, not pointers, so that the callers form no generic pointers on the straight line)
-template <uint32_t DB>
+template <uint32_t DB, int RB>
 __device__ __noinline__ void dense_word_slow(uint32_t F, uint32_t t, uint32_t tprev, int valid, uint32_t s_out_addr) {
-    uint32_t *ohash = reinterpret_cast<uint32_t *>(__cvta_shared_to_generic(DB + DENSE_WORDS * 4u));
+    uint32_t *ohash = reinterpret_cast<uint32_t *>(__cvta_shared_to_generic(DB + Dense<RB>::REGION));
     volatile uint32_t *s_out = reinterpret_cast<volatile uint32_t *>(__cvta_shared_to_generic(s_out_addr));
     uint32_t tp = tprev >> 24;
     for (int j = 0; j < 4; j++) {
         const uint32_t tj = (t >> (8 * j)) & 255u;
         if (j < valid) {
-            if (((tp | tj) & 0xE0u) == 0) {
-                smem_inc(DB + dense_off(F, tp, tj));
+            if (((tp | tj) & Dense<RB>::OUT) == 0) {
+                smem_inc(DB + dense_off<RB>(F, tp, tj));
             } else if (s_out[F] == 0) {
                 // outliers go to the trial's hash table until an insert finds it crowded; from then on the
                 // trial is flagged and all its outliers are counted in h0 after the barrier
-                if (!ohash_add(ohash + (F - 1) * HSLOTS, (((tp + 240u) & 255u) << 8) | ((tj + 240u) & 255u)))
+                // (the key is the pair of residual bytes; never 0, since one of them lies outside the range)
+                if (!ohash_add(ohash + (F - 1) * HSLOTS, (((tp - Dense<RB>::HALF) & 255u) << 8) | ((tj - Dense<RB>::HALF) & 255u)))
                     s_out[F] = 1u;
             }
         }
@@ -617,40 +650,40 @@ __device__ __noinline__ void dense_word_slow(uint32_t F, uint32_t t, uint32_t tp
 
 // trial 0 on coarse keys (low five bits of both raw bytes): 32x32 counters in the even 128-byte lines of the 8 KB at
 // COARSE_OFF; offset first << 8 | ((second ^ first) & 31) << 2, i.e. high byte = first, low byte = bank << 2
-template <uint32_t DB>
+template <uint32_t DB, int RB>
 __device__ __forceinline__ void dense_word0(uint32_t x, uint32_t xpw) {
     const uint32_t hi = xpw & 0x1F1F1F1Fu;
     const uint32_t lo = ((x ^ xpw) & 0x1F1F1F1Fu) << 2;
-    smem_inc_at<DB + COARSE_OFF>(prmt(lo, hi, 0xCC40u));
-    smem_inc_at<DB + COARSE_OFF>(prmt(lo, hi, 0xDD51u));
-    smem_inc_at<DB + COARSE_OFF>(prmt(lo, hi, 0xEE62u));
-    smem_inc_at<DB + COARSE_OFF>(prmt(lo, hi, 0xFF73u));
+    smem_inc_at<DB + Dense<RB>::COARSE>(prmt(lo, hi, 0xCC40u));
+    smem_inc_at<DB + Dense<RB>::COARSE>(prmt(lo, hi, 0xDD51u));
+    smem_inc_at<DB + Dense<RB>::COARSE>(prmt(lo, hi, 0xEE62u));
+    smem_inc_at<DB + Dense<RB>::COARSE>(prmt(lo, hi, 0xFF73u));
 }
-template <uint32_t DB>
+template <uint32_t DB, int RB>
 __device__ __noinline__ void dense_word0_slow(uint32_t x, uint32_t xprev, int valid) {
     uint32_t p = (xprev >> 24) & 31u;
     for (int j = 0; j < valid && j < 4; j++) {
         const uint32_t b = (x >> (8 * j)) & 31u;
-        smem_inc(DB + COARSE_OFF + ((p << 8) | ((b ^ p) << 2)));
+        smem_inc(DB + Dense<RB>::COARSE + ((p << 8) | ((b ^ p) << 2)));
         p = b;
     }
 }
 // the last, partial pair of a row (fewer than eight valid bytes): everything window by window
-template <uint32_t DB>
+template <uint32_t DB, int RB>
 __device__ __noinline__ void dense_pair_tail(uint32_t x0, uint32_t x1, uint32_t xprev, uint32_t t10, uint32_t t11, uint32_t t20,
                                              uint32_t t21, uint32_t t30, uint32_t t31, uint32_t t40, uint32_t t41, uint32_t tp1,
                                              uint32_t tp2, uint32_t tp3, uint32_t tp4, int valid0, uint32_t s_out_addr) {
-    dense_word0_slow<DB>(x0, xprev, valid0);
-    dense_word_slow<DB>(1u, t10, tp1, valid0, s_out_addr);
-    dense_word_slow<DB>(2u, t20, tp2, valid0, s_out_addr);
-    dense_word_slow<DB>(3u, t30, tp3, valid0, s_out_addr);
-    dense_word_slow<DB>(4u, t40, tp4, valid0, s_out_addr);
+    dense_word0_slow<DB, RB>(x0, xprev, valid0);
+    dense_word_slow<DB, RB>(1u, t10, tp1, valid0, s_out_addr);
+    dense_word_slow<DB, RB>(2u, t20, tp2, valid0, s_out_addr);
+    dense_word_slow<DB, RB>(3u, t30, tp3, valid0, s_out_addr);
+    dense_word_slow<DB, RB>(4u, t40, tp4, valid0, s_out_addr);
     if (valid0 > 4) {
-        dense_word0_slow<DB>(x1, x0, valid0 - 4);
-        dense_word_slow<DB>(1u, t11, t10, valid0 - 4, s_out_addr);
-        dense_word_slow<DB>(2u, t21, t20, valid0 - 4, s_out_addr);
-        dense_word_slow<DB>(3u, t31, t30, valid0 - 4, s_out_addr);
-        dense_word_slow<DB>(4u, t41, t40, valid0 - 4, s_out_addr);
+        dense_word0_slow<DB, RB>(x1, x0, valid0 - 4);
+        dense_word_slow<DB, RB>(1u, t11, t10, valid0 - 4, s_out_addr);
+        dense_word_slow<DB, RB>(2u, t21, t20, valid0 - 4, s_out_addr);
+        dense_word_slow<DB, RB>(3u, t31, t30, valid0 - 4, s_out_addr);
+        dense_word_slow<DB, RB>(4u, t41, t40, valid0 - 4, s_out_addr);
     }
 }
 
@@ -701,7 +734,7 @@ __device__ __noinline__ void bigram_exact0(const uint8_t *cur, uint32_t len, uin
 // Exact for any data: every window is counted in exactly one structure, and their key sets are disjoint.
 // Flagged trials (their outlier hash crowded in this row): the outlier windows, re-derived from the staged row, are
 // counted in h0, one trial at a time.  Off the straight line: kept out of line for the instruction cache.
-template <int D, int NT>
+template <int D, int NT, int RB>
 __device__ __noinline__ void bigram_flagged(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
                                             const Smem &sm, uint32_t h0_slots, uint32_t flagged) {
     const uint32_t nwords = (len + 3) >> 2, lane = threadIdx.x & 31u;
@@ -729,7 +762,7 @@ __device__ __noinline__ void bigram_flagged(const uint8_t *cur, const uint8_t *u
             const int valid = (int)len - 4 * kk;
             for (int j = 0; j < 4 && j < valid; j++) {
                 const uint32_t b = (r >> (8 * j)) & 255u;
-                if ((((pr + 16u) | (b + 16u)) & 0xE0u) != 0) h0_add(h0, (pr << 8) | b, hshift, hmask);
+                if ((((pr + Dense<RB>::HALF) | (b + Dense<RB>::HALF)) & Dense<RB>::OUT) != 0) h0_add(h0, (pr << 8) | b, hshift, hmask);
                 pr = b;
             }
         }
@@ -746,7 +779,7 @@ __device__ __noinline__ void bigram_flagged(const uint8_t *cur, const uint8_t *u
     }
 }
 
-template <int D, int NT, uint32_t DB>
+template <int D, int NT, uint32_t DB, int RB>
 __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift, int bpp,
                                                      const Smem &sm, uint32_t h0_slots, const Prefetch &pf) {
     static_assert(NT % 128 == 0, "the sweep gives every trial NT / 128 whole warps");
@@ -776,7 +809,7 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
         uint32_t t[4][2];
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-            const uint32_t xc = __vadd4(x[i], 0x10101010u);
+            const uint32_t xc = __vadd4(x[i], Dense<RB>::HALF * 0x01010101u);
             t[0][i] = __vsub4(xc, l[i]);
             t[1][i] = __vsub4(xc, u[i]);
             t[2][i] = __vsub4(xc, __vhaddu4(l[i], u[i]));
@@ -791,15 +824,15 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
             if (k == 0) {
                 xprev = 0;
 #pragma unroll
-                for (int f = 0; f < 4; f++) tprev[f] = (uint32_t)(f + 1 + 16) << 24;
+                for (int f = 0; f < 4; f++) tprev[f] = ((uint32_t)(f + 1) + Dense<RB>::HALF) << 24;
             } else if (pr < npairs) {
                 const int q = 4 * k - 1;
                 const uint32_t cx = cur[q], cl = cur[q - bpp], cu = up[q], cul = up[q - bpp];
                 xprev = cx << 24;
-                tprev[0] = (cx - cl + 16u) << 24;
-                tprev[1] = (cx - cu + 16u) << 24;
-                tprev[2] = (cx - ((cl + cu) >> 1) + 16u) << 24;
-                tprev[3] = (cx - paeth(cl, cu, cul) + 16u) << 24;
+                tprev[0] = (cx - cl + Dense<RB>::HALF) << 24;
+                tprev[1] = (cx - cu + Dense<RB>::HALF) << 24;
+                tprev[2] = (cx - ((cl + cu) >> 1) + Dense<RB>::HALF) << 24;
+                tprev[3] = (cx - paeth(cl, cu, cul) + Dense<RB>::HALF) << 24;
             }
         }
         if (pr < npairs) {
@@ -809,24 +842,24 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     // "bytes in front" word: byte m is m ? word.byte[m-1] : previous word.byte[3]
-                    dense_word0<DB>(x[i], prmt(x[i], i ? x[0] : xprev, 0x2107u));
+                    dense_word0<DB, RB>(x[i], prmt(x[i], i ? x[0] : xprev, 0x2107u));
 #pragma unroll
                     for (int f = 0; f < 4; f++) {
                         const uint32_t tp = i ? t[f][0] : tprev[f];
                         const uint32_t tpw = prmt(t[f][i], tp, 0x2107u);
-                        if (((t[f][i] | tpw) & 0xE0E0E0E0u) == 0) { // the common case: all four windows in range
-                            if (f == 0) dense_word<1, DB>(t[f][i], tpw);
-                            if (f == 1) dense_word<2, DB>(t[f][i], tpw);
-                            if (f == 2) dense_word<3, DB>(t[f][i], tpw);
-                            if (f == 3) dense_word<4, DB>(t[f][i], tpw);
+                        if (((t[f][i] | tpw) & Dense<RB>::OUT4) == 0) { // the common case: all four windows in range
+                            if (f == 0) dense_word<1, DB, RB>(t[f][i], tpw);
+                            if (f == 1) dense_word<2, DB, RB>(t[f][i], tpw);
+                            if (f == 2) dense_word<3, DB, RB>(t[f][i], tpw);
+                            if (f == 3) dense_word<4, DB, RB>(t[f][i], tpw);
                         } else {
-                            dense_word_slow<DB>((uint32_t)f + 1u, t[f][i], tp, 4, s_out_addr);
+                            dense_word_slow<DB, RB>((uint32_t)f + 1u, t[f][i], tp, 4, s_out_addr);
                         }
                     }
                 }
             } else {
                 nz |= (x[0] & tail_mask(valid0)) | (x[1] & tail_mask(valid0 - 4));
-                dense_pair_tail<DB>(x[0], x[1], xprev, t[0][0], t[0][1], t[1][0], t[1][1], t[2][0], t[2][1], t[3][0], t[3][1],
+                dense_pair_tail<DB, RB>(x[0], x[1], xprev, t[0][0], t[0][1], t[1][0], t[1][1], t[2][0], t[2][1], t[3][0], t[3][1],
                                     tprev[0], tprev[1], tprev[2], tprev[3], valid0, s_out_addr);
             }
         }
@@ -841,9 +874,10 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
         uint4 *dn = reinterpret_cast<uint4 *>(sm.small);
         const uint32_t warp = threadIdx.x >> 5, f = 1u + warp / WPT;
         uint32_t d = 0, e = 0;
-        // c = first : 5 | group of four seconds : 3
-        for (uint32_t c = (warp % WPT) * 32u + lane; c < 256u; c += WPT * 32u) {
-            uint4 *cell = dn + (c >> 3) * 32u + (f - 1u) * 8u + (c & 7u);
+        // c = first : RB | group of four seconds : RB - 2
+        constexpr uint32_t G = RB - 2;
+        for (uint32_t c = (warp % WPT) * 32u + lane; c < (1u << (2 * RB - 2)); c += WPT * 32u) {
+            uint4 *cell = dn + (c >> G) * (4u << G) + (f - 1u) * (1u << G) + (c & ((1u << G) - 1u));
             const uint4 a = *cell;
             *cell = make_uint4(0, 0, 0, 0);
             d += (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0);
@@ -871,7 +905,7 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
         }
         // trial 0 (coarse keys): 1024 counters in 32 lines of 128 bytes (every other line of the 8 KB at COARSE_OFF)
         {
-            uint4 *d4 = dn + COARSE_OFF / 16u;
+            uint4 *d4 = dn + Dense<RB>::COARSE / 16u;
             uint32_t d0 = 0, e0 = 0;
             for (uint32_t q = threadIdx.x; q < 256u; q += NT) {
                 uint4 *cell = d4 + (q >> 3) * 16u + (q & 7u);
@@ -893,7 +927,7 @@ __device__ __forceinline__ uint32_t bigram_row_small(const uint8_t *cur, const u
     // flagged trials: their outlier windows, re-derived from the staged row, are counted in h0, one trial at a time
     const uint32_t flagged = sm.s_out_()[1] | sm.s_out_()[2] << 1 | sm.s_out_()[3] << 2 | sm.s_out_()[4] << 3; // uniform
     if (flagged == 0) return nz;
-    bigram_flagged<D, NT>(cur, up, len, shift, bpp, sm, h0_slots, flagged);
+    bigram_flagged<D, NT, RB>(cur, up, len, shift, bpp, sm, h0_slots, flagged);
     return nz;
 }
 
@@ -1184,7 +1218,7 @@ __device__ __noinline__ int decide_row(const DevStrategy &st, uint32_t r, uint32
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 template <int D, int SC>
-__global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? ((SC & SC_ENTROPY) ? HALF_OCC - 1 : HALF_OCC) : (SC & SC_BIGRAM) ? 1 : (SC == SC_MINSUM || SC == 0) ? 3 : 2) k_fast(const __grid_constant__ FastParams P) {
+__global__ void __launch_bounds__(threads_for(SC), (SC & SC_WIDE) ? 2 : (SC & SC_HALF) ? ((SC & SC_ENTROPY) ? HALF_OCC - 1 : HALF_OCC) : (SC & SC_BIGRAM) ? 1 : (SC == SC_MINSUM || SC == 0) ? 3 : 2) k_fast(const __grid_constant__ FastParams P) {
     constexpr int NT = threads_for(SC);
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t NS = P.nslot;
@@ -1207,7 +1241,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? ((SC & SC_EN
     if (SC & SC_BIGRAM) {
         for (uint32_t i = tid; i < (P.small_tab == 1u ? P.h0_slots : split ? SPLIT_BYTES / 4 : 32768u); i += NT) sm.table[i] = 0;
         if (P.small_tab == 1u)
-            for (uint32_t i = tid; i < SMALL_BYTES / 4; i += NT) sm.small[i] = 0;
+            for (uint32_t i = tid; i < Dense<rb_of(SC)>::SMALL / 4; i += NT) sm.small[i] = 0;
     }
     __syncthreads();
 
@@ -1228,6 +1262,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? ((SC & SC_EN
     for (uint64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
         const uint64_t img = item / P.items_per_image;
         const uint32_t it = (uint32_t)(item % P.items_per_image);
+        if (P.img_class && P.img_class[img] != P.want_class) continue; // another launch (other table range) takes this image
         int p = 0;
 #pragma unroll
         for (int i = 1; i < 7; i++)
@@ -1318,7 +1353,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_HALF) ? ((SC & SC_EN
                         split_done = true;
                     }
                     else if ((SC & SC_HALF) || P.small_tab == 1u) {
-                        nz |= bigram_row_small<D, NT, SMEM_WIN + SMEM_HDR + ((SC & SC_ENTROPY) ? 5u * HIST_REP * 256u * 4u : 0u)>(cur, up, len, shift, bpp, sr, P.h0_slots, pf);
+                        nz |= bigram_row_small<D, NT, SMEM_WIN + SMEM_HDR + ((SC & SC_ENTROPY) ? 5u * HIST_REP * 256u * 4u : 0u), rb_of(SC)>(cur, up, len, shift, bpp, sr, P.h0_slots, pf);
                         small_flow = true;
                     }
                     else if (wpt <= 1) bigram_row<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
@@ -1764,6 +1799,7 @@ KernelFn pick_sc(int sc) {
     case SC_ENTROPY: return k_fast<D, SC_ENTROPY>;
     case SC_BIGRAM: return k_fast<D, SC_BIGRAM>;
     case SC_BIGRAM | SC_HALF: return k_fast<D, SC_BIGRAM | SC_HALF>;
+    case SC_BIGRAM | SC_HALF | SC_WIDE: return k_fast<D, SC_BIGRAM | SC_HALF | SC_WIDE>;
     case SC_ENTROPY | SC_BIGRAM: return k_fast<D, SC_ENTROPY | SC_BIGRAM>;
     case SC_ENTROPY | SC_BIGRAM | SC_HALF: return k_fast<D, SC_ENTROPY | SC_BIGRAM | SC_HALF>;
     default: return k_fast<D, SC_MINSUM | SC_ENTROPY | SC_BIGRAM>;
@@ -1813,10 +1849,10 @@ __global__ void k_probe_smem_window(uint32_t *out) {
 cudaError_t fast_tier_init(int device, uint32_t *smem_window) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
-    const int scs[8] = {0, SC_MINSUM, SC_ENTROPY, SC_BIGRAM, SC_BIGRAM | SC_HALF, SC_ENTROPY | SC_BIGRAM,
-                        SC_ENTROPY | SC_BIGRAM | SC_HALF, SC_MINSUM | SC_ENTROPY | SC_BIGRAM};
+    const int scs[9] = {0, SC_MINSUM, SC_ENTROPY, SC_BIGRAM, SC_BIGRAM | SC_HALF, SC_BIGRAM | SC_HALF | SC_WIDE,
+                        SC_ENTROPY | SC_BIGRAM, SC_ENTROPY | SC_BIGRAM | SC_HALF, SC_MINSUM | SC_ENTROPY | SC_BIGRAM};
     for (int d = 0; d < 3; d++)
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < 9; i++) {
             e = cudaFuncSetAttribute((const void *)pick_kernel(d, scs[i]), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)SMEM_LIMIT);
             if (e != cudaSuccess) return e;
@@ -1890,9 +1926,11 @@ bool fast_supported(const Geom &g, const StrategySet &set) {
     return true;
 }
 
-cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_data, size_t n_images,
-                        const StrategySet &set) {
-    int sc = kernel_sc(scorers_needed(set));
+// One launch of the fast tier for scorer set `sc` (SC_HALF / SC_WIDE chosen by the caller).  img_class != nullptr: only the
+// images of class want_class are processed (the other class belongs to a second launch).
+static cudaError_t launch_fast_variant(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_data, size_t n_images,
+                                       const StrategySet &set, int sc, bool small_tab, bool split, uint32_t h0,
+                                       const uint8_t *img_class, uint32_t want_class) {
     FastParams P;
     P.g = g;
     P.set = set;
@@ -1900,25 +1938,15 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
     P.n_images = n_images;
     P.rb = slot_bytes(g);
     P.shift = 8 * (g.bpp % 4);
-    // bigram scorer, rows <= 16384 bytes: dense tables + outlier hashes + hash of whole rows (>= 2 slots per window)
-    uint32_t h0 = 1024;
-    while (h0 < 2 * g.max_len) h0 *= 2;
-    P.small_tab = (sc & SC_BIGRAM) && g.max_len <= 16384 && smem_bytes_for(sc, P.rb, h0) <= SMEM_LIMIT;
-    P.h0_slots = P.small_tab ? h0 : 0;
-    // longer rows (<= 32 KB; mostly 16-bit images): the split-table layout, see bigram_row_split
-    const bool split = sc == SC_BIGRAM && !P.small_tab && g.max_len <= 32768 && smem_bytes_for(sc, P.rb, 0, 3, true) <= SMEM_LIMIT;
-    if (split) P.small_tab = 2;
-    // ... and with rows <= 4096 bytes two 512-thread CTAs fit an SM (two rows in flight: one CTA's barriers and table
-    // sweeps overlap the other's counting)
-    // (with the Entropy histograms resident as well: three CTAs per SM)
-    const uint32_t half_occ = (sc & SC_ENTROPY) ? HALF_OCC - 1 : HALF_OCC;
-    const uint32_t two_per_sm = (233472u / half_occ - 1024u) & ~127u; // shared memory of one of half_occ resident CTAs
-    if ((sc == SC_BIGRAM || sc == (SC_ENTROPY | SC_BIGRAM)) && P.small_tab && g.max_len <= 4096 &&
-        smem_bytes_for(sc | SC_HALF, P.rb, h0, 3) <= two_per_sm)
-        sc |= SC_HALF;
+    P.small_tab = split ? 2 : small_tab ? 1 : 0;
+    P.h0_slots = small_tab ? h0 : 0;
+    P.img_class = img_class;
+    P.want_class = want_class;
     const int nt = threads_for(sc);
+    const uint32_t half_occ = (sc & SC_WIDE) ? 2 : (sc & SC_ENTROPY) ? HALF_OCC - 1 : HALF_OCC;
+    const uint32_t per_cta = (233472u / half_occ - 1024u) & ~127u; // shared memory of one of half_occ resident CTAs
     // a fourth ring slot removes the end-of-row barrier; take it when it does not cost occupancy (rows <= 16 KB)
-    const uint32_t budget = (sc & SC_HALF) ? two_per_sm : SMEM_LIMIT;
+    const uint32_t budget = (sc & SC_HALF) ? per_cta : SMEM_LIMIT;
     P.nslot = (sc != 0 && !split && P.rb <= 16448 && smem_bytes_for(sc, P.rb, P.h0_slots, 4) <= budget) ? 4 : 3;
     const uint32_t smem = smem_bytes_for(sc, P.rb, P.h0_slots, P.nslot, split);
     KernelFn fn = pick_kernel((int)(g.bpp / 4), sc);
@@ -1975,6 +2003,79 @@ cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_da
     fn<<<(unsigned)grid, nt, smem, ctx.stream>>>(P);
     count_launch();
     return cudaGetLastError();
+}
+
+// Spread of an image's filtered rows, sampled: class 1 when in eight rows of the first pass more than SPREAD_PCT percent of
+// the bytes have their Sub residual outside [-16, 15] and as many their Up residual -- such rows put most windows on the
+// slow outlier path of the 32 x 32 tables (measured 6x slower at +-12 of noise); the 64 x 64 tables take them instead.
+constexpr uint32_t SPREAD_PCT = 4;
+__global__ void __launch_bounds__(256) k_spread_probe(Geom g, const uint8_t *__restrict__ data, uint64_t n_images,
+                                                      uint8_t *__restrict__ img_class) {
+    __shared__ uint32_t s_cnt[2];
+    for (uint64_t img = blockIdx.x; img < n_images; img += gridDim.x) {
+        if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = 0;
+        __syncthreads();
+        const PassDesc pd = g.pass[0];
+        const uint8_t *base = data + img * g.data_len + pd.in_base;
+        uint32_t cs = 0, cu = 0, total = 0;
+        if (pd.nrows >= 2) {
+            for (uint32_t sidx = 0; sidx < 8; sidx++) {
+                uint32_t r = (uint32_t)(((uint64_t)pd.nrows * (2 * sidx + 1)) / 16);
+                if (r == 0) r = 1;
+                const uint8_t *row = base + (size_t)r * pd.len, *up = row - pd.len;
+                for (uint32_t i = g.bpp + threadIdx.x; i < pd.len; i += 256) {
+                    const uint32_t x = row[i];
+                    const uint32_t rs = (x - row[i - g.bpp] + 16u) & 255u, ru = (x - up[i] + 16u) & 255u;
+                    cs += rs >= 32u;
+                    cu += ru >= 32u;
+                }
+                total += pd.len > g.bpp ? pd.len - g.bpp : 0;
+            }
+        }
+        cs = warp_sum(cs);
+        cu = warp_sum(cu);
+        if ((threadIdx.x & 31) == 0 && (cs | cu)) {
+            atomicAdd(&s_cnt[0], cs);
+            atomicAdd(&s_cnt[1], cu);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            img_class[img] = (uint64_t)min(s_cnt[0], s_cnt[1]) * 100u > (uint64_t)SPREAD_PCT * total ? 1 : 0;
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_fast(const LaunchCtx &ctx, const Geom &g, const uint8_t *d_data, size_t n_images,
+                        const StrategySet &set) {
+    int sc = kernel_sc(scorers_needed(set));
+    const uint32_t rb = slot_bytes(g);
+    // bigram scorer, rows <= 16384 bytes: dense tables + outlier hashes + hash of whole rows (>= 2 slots per window)
+    uint32_t h0 = 1024;
+    while (h0 < 2 * g.max_len) h0 *= 2;
+    const bool small_tab = (sc & SC_BIGRAM) && g.max_len <= 16384 && smem_bytes_for(sc, rb, h0) <= SMEM_LIMIT;
+    // longer rows (<= 32 KB; mostly 16-bit images): the split-table layout, see bigram_row_split
+    const bool split = sc == SC_BIGRAM && !small_tab && g.max_len <= 32768 && smem_bytes_for(sc, rb, 0, 3, true) <= SMEM_LIMIT;
+    // ... and with rows <= 4096 bytes several small CTAs fit an SM (rows in flight side by side: one CTA's barriers and
+    // table sweeps overlap the others' counting): four of 256 threads, three with the Entropy histograms resident as well
+    const uint32_t half_occ = (sc & SC_ENTROPY) ? HALF_OCC - 1 : HALF_OCC;
+    const uint32_t per_cta = (233472u / half_occ - 1024u) & ~127u;
+    if ((sc == SC_BIGRAM || sc == (SC_ENTROPY | SC_BIGRAM)) && small_tab && g.max_len <= 4096 &&
+        smem_bytes_for(sc | SC_HALF, rb, h0, 3) <= per_cta)
+        sc |= SC_HALF;
+    // Bigrams/BigEnt on short rows: the images are classed by the spread of their residuals on the device (no host round
+    // trip), and two launches share the batch -- 32 x 32 tables for class 0, 64 x 64 tables for class 1
+    if (sc == (SC_BIGRAM | SC_HALF) && ctx.scratch && ctx.scratch_bytes >= n_images &&
+        smem_bytes_for(sc | SC_WIDE, rb, h0, 3) <= ((233472u / 2 - 1024u) & ~127u)) {
+        uint64_t pg = n_images < (uint64_t)ctx.num_sms * 8 ? n_images : (uint64_t)ctx.num_sms * 8;
+        k_spread_probe<<<(unsigned)pg, 256, 0, ctx.stream>>>(g, d_data, n_images, ctx.scratch);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        e = launch_fast_variant(ctx, g, d_data, n_images, set, sc, small_tab, false, h0, ctx.scratch, 0);
+        if (e != cudaSuccess) return e;
+        return launch_fast_variant(ctx, g, d_data, n_images, set, sc | SC_WIDE, small_tab, false, h0, ctx.scratch, 1);
+    }
+    return launch_fast_variant(ctx, g, d_data, n_images, set, sc, small_tab, split, h0, nullptr, 0);
 }
 
 } // namespace oxi

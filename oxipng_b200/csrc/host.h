@@ -32,6 +32,11 @@ struct Slot {
     size_t out_cap = 0;
     uint8_t *d_pre = nullptr;
     size_t pre_cap = 0;
+    // pinned staging for callers with ordinary (pageable) host memory -- what `&[u8]` / `Vec<u8>` give the Rust side
+    uint8_t *h_in = nullptr, *h_out = nullptr;
+    size_t h_in_cap = 0, h_out_cap = 0;
+    struct Pending { uint8_t *dst; const uint8_t *src; size_t n; };
+    std::vector<Pending> pending; // staged results to copy out to the caller once the stream has finished
 };
 
 struct DeviceCtx {

@@ -459,3 +459,34 @@ def test_alpha_tier_staged_rows():
             wnt, wu, _ = oracle.filter_image((200, 25, 6, 8, 0), imgs[i], k, b, None, True)
             assert np.array_equal(outs[j][i * per:(i + 1) * per], wnt), (i, j)
             assert np.array_equal(used[j][i * 25:(i + 1) * 25], wu), (i, j)
+
+
+def test_bigram_wide_tables_and_image_classes():
+    """Batches whose images differ in residual spread: k_spread_probe classes them on the device and two launches share the
+    batch (32 x 32 tables / 64 x 64 tables, k_fast<.., SC_BIGRAM|SC_HALF|SC_WIDE>).  Noise of +-4 .. +-60 and pure noise,
+    ragged widths, every bpp class, plus spikes beyond +-32 (outlier hashes of the wide tables)."""
+    import oxipng_b200 as ox
+    rng = np.random.default_rng(2024)
+    for (w, h, ct, bd) in [(256, 24, 6, 8), (300, 17, 2, 8), (1000, 9, 0, 8), (511, 12, 4, 8), (250, 10, 6, 16)]:
+        ih0, base = helpers.synth_image(w, h, ct, bd, 5, "photo")
+        imgs = []
+        for amp in (0, 4, 10, 12, 20, 31, 40, 60, 128):
+            d = np.frombuffer(bytes(base), np.uint8).astype(np.int64)
+            if amp:
+                d = (d + rng.integers(-amp, amp + 1, size=d.size)) & 255
+            d = d.astype(np.uint8)
+            if amp in (12, 31):
+                d[rng.choice(d.size, size=d.size // 50, replace=False)] = 255  # far-out spikes
+            imgs.append(d)
+        hdr = helpers.product_image(ih0, imgs[0]).ihdr
+        S = ox.FilterStrategy
+        for strat, kinds in (([S.NONE, S.Bigrams, S.BigEnt], [(oracle.BASIC, 0), (oracle.BIGRAMS, 0), (oracle.BIGENT, 0)]),
+                             ([S.BigEnt], [(oracle.BIGENT, 0)])):
+            outs, used = ox.filter_batch(hdr, np.concatenate(imgs), len(imgs), strat, False, ox.FLAG_FORCE_FAST)
+            rows = len(helpers.product_image(ih0, imgs[0]).scan_lines())
+            per = imgs[0].size + rows
+            for i, d in enumerate(imgs):
+                for j, (k, b) in enumerate(kinds):
+                    want, wu, _ = oracle.filter_image(ih0, d, k, b)
+                    assert np.array_equal(used[j][i * rows:(i + 1) * rows], wu), (w, ct, bd, i, j)
+                    assert np.array_equal(outs[j][i * per:(i + 1) * per], want), (w, ct, bd, i, j)
