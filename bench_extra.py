@@ -147,25 +147,27 @@ def batch_configs(ox, synth, torch, dev, local, stream, peak, iters, n_images=25
         nz[3::4] = 0
         return ((base.to(torch.int16) + nz) & 255).to(torch.uint8)
 
-    def transparent():  # 10 % of the 16x16 blocks fully transparent with random colour behind (optimize_alpha's target)
+    def transparent(n):  # 10 % of the 16x16 blocks fully transparent with random colour behind (optimize_alpha's target)
         g = torch.Generator(device=dev)
         g.manual_seed(9)
-        d = base.clone().view(n_images, h, w, 4)
-        blk = torch.rand((n_images, h // 16, w // 16), device=dev, generator=g) < 0.10
+        reps = -(-n // n_images)
+        d = base.repeat(reps)[: n * per].clone().view(n, h, w, 4)
+        blk = torch.rand((n, h // 16, w // 16), device=dev, generator=g) < 0.10
         m = blk.repeat_interleave(16, 1).repeat_interleave(16, 2)
-        rnd = torch.randint(0, 256, (n_images, h, w, 3), dtype=torch.uint8, device=dev, generator=g)
+        rnd = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=dev, generator=g)
         d[..., :3] = torch.where(m[..., None], rnd, d[..., :3])
         d[..., 3] = torch.where(m, torch.zeros_like(d[..., 3]), d[..., 3])
         return d.reshape(-1).contiguous()
 
+    # optimize_alpha chains are serial per (image, strategy): the batches are sized to whole waves of resident chains
+    # (148 SMs x 4 CTAs = 592)
     cfgs = [
         ("o2_default_set_none_sub_entropy_bigrams_1024", base, [S.NONE, S.SUB, S.Entropy, S.Bigrams], False, n_images),
         ("evaluator_set_none_bigrams_1024", base, [S.NONE, S.Bigrams], False, n_images),
         ("c5_noise6_none_bigrams_bigent_1024", noisy(6), [S.NONE, S.Bigrams, S.BigEnt], False, n_images),
         ("c5_noise12_none_bigrams_bigent_1024", noisy(12), [S.NONE, S.Bigrams, S.BigEnt], False, n_images),
-        ("alpha_optimize_minsum_rgba8_1024_10pct_transparent", transparent(), [S.MinSum], True, n_images),
-        ("alpha_optimize_o2_set_rgba8_1024_10pct_transparent", None, [S.NONE, S.SUB, S.Entropy, S.Bigrams], True,
-         n_images),
+        ("alpha_optimize_minsum_rgba8_1024_10pct_transparent", transparent(592), [S.MinSum], True, 592),
+        ("alpha_optimize_o2_set_rgba8_1024_10pct_transparent", None, [S.NONE, S.SUB, S.Entropy, S.Bigrams], True, 296),
     ]
     last_alpha = None
     for name, d, strat, alpha, n in cfgs:
@@ -306,20 +308,35 @@ def o2_flow(ox, torch, dev, local, stream):
             i = png.ihdr
             self.tried.append((description, i.color_type.code, int(i.bit_depth), png.data.size))
 
+    trial_filters = [S.NONE, S.SUB, S.Entropy, S.Bigrams]  # Options::default().filter (options.rs:282-287): perform_trials
+
     def run(kind):
         ev = Timed(Evaluator(filters, zlib_level=6, threads=os.cpu_count() or 8))
         t = time.perf_counter()
         if kind == "resident":
-            perform_reductions(rb.upload(img, local, stream.cuda_stream), Options(), ev, backend=rb, interlacer=rb.change_interlacing)
+            base = perform_reductions(rb.upload(img, local, stream.cuda_stream), Options(), ev, backend=rb, interlacer=rb.change_interlacing)
         else:
-            perform_reductions(img, Options(), ev, backend=R, interlacer=ox.change_interlacing)
+            base = perform_reductions(img, Options(), ev, backend=R, interlacer=ox.change_interlacing)
         total = time.perf_counter() - t
         best = ev.inner.get_best_candidate()
-        return total, ev.t, ev.tried, best
+        # perform_trials (lib.rs:437-520): the chosen image through the full filter set; the filtered streams are what
+        # crosses PCIe, deflate (zlib here) stays on the host threads
+        chosen = best.image if best is not None else base
+        t = time.perf_counter()
+        if hasattr(chosen, "filter_image_multi"):
+            outs, used = chosen.filter_image_multi(trial_filters, False)
+        else:
+            outs, used = ox.filter_image_multi(chosen, trial_filters, False)
+        t_filter = time.perf_counter() - t
+        import hashlib
+        h = hashlib.sha256()
+        for o in outs:
+            h.update(o.tobytes())
+        return total, ev.t, ev.tried, best, t_filter, h.hexdigest()
 
     run("resident")
-    res_t, res_ev, res_tried, res_best = min((run("resident") for _ in range(3)), key=lambda r: r[0])
-    host_t, host_ev, host_tried, host_best = min((run("host") for _ in range(2)), key=lambda r: r[0])
+    res_t, res_ev, res_tried, res_best, res_tf, res_sha = min((run("resident") for _ in range(3)), key=lambda r: r[0])
+    host_t, host_ev, host_tried, host_best, host_tf, host_sha = min((run("host") for _ in range(2)), key=lambda r: r[0])
 
     # oracle-driven CPU flow (checker + CPU time beside it)
     class OracleEvaluator(Evaluator):
@@ -342,20 +359,37 @@ def o2_flow(ox, torch, dev, local, stream):
     oracle.use_native()
     oev = Timed(OracleEvaluator(filters, zlib_level=6, threads=os.cpu_count() or 8))
     t = time.perf_counter()
-    perform_reductions(img, Options(), oev, backend=helpers.OracleReductions(), interlacer=helpers.oracle_change_interlacing)
+    obase = perform_reductions(img, Options(), oev, backend=helpers.OracleReductions(), interlacer=helpers.oracle_change_interlacing)
     cpu_t = time.perf_counter() - t
     obest = oev.inner.get_best_candidate()
+    ochosen = obest.image if obest is not None else obase
+    import concurrent.futures as cf
+    import hashlib
+    t = time.perf_counter()
+    with cf.ThreadPoolExecutor(max_workers=4) as ex:
+        oouts = list(ex.map(lambda s_: oracle.filter_image(helpers._img_tuple(ochosen), ochosen.data, *_oracle_kind(s_))[0], trial_filters))
+    cpu_tf = time.perf_counter() - t
+    oh = hashlib.sha256()
+    for o in oouts:
+        oh.update(o.tobytes())
+    o_sha = oh.hexdigest()
 
     def sig(b):
         return None if b is None else (b.image.ihdr.color_type.code, int(b.image.ihdr.bit_depth), b.image.data.size,
                                        b.estimated_output_size, b.filter.kind)
-    parity = res_tried == oev.tried and host_tried == oev.tried and sig(res_best) == sig(obest) and sig(host_best) == sig(obest)
+    parity = (res_tried == oev.tried and host_tried == oev.tried and sig(res_best) == sig(obest) and sig(host_best) == sig(obest)
+              and res_sha == o_sha and host_sha == o_sha)
     return {"image": "2048x2048 RGBA8, 256 colours", "filters": ["None", "Bigrams"], "candidates": len(res_tried),
             "ms": (res_t - res_ev) * 1e3, "resident_total_ms": res_t * 1e3,
             "resident_reductions_ms": (res_t - res_ev) * 1e3, "resident_evaluator_ms": res_ev * 1e3,
             "host_buffer_total_ms": host_t * 1e3, "host_buffer_reductions_ms": (host_t - host_ev) * 1e3,
             "cpu_oracle_flow_ms": cpu_t * 1e3, "cpu_oracle_reductions_ms": (cpu_t - oev.t) * 1e3,
             "evaluator_note": "evaluator time includes zlib level 6 on the host threads (stand-in for libdeflater)",
+            "trial_filters": ["None", "Sub", "Entropy", "Bigrams"], "trial_image_bytes": int(ochosen.data.size),
+            "resident_trial_filter_ms": res_tf * 1e3, "host_buffer_trial_filter_ms": host_tf * 1e3,
+            "cpu_oracle_trial_filter_ms": cpu_tf * 1e3,
+            "trial_note": "perform_trials' filter fan-out on the image the reductions chose: resident = kernels + D2H of the four "
+                          "filtered streams only; host buffers = upload + kernels + download; CPU = oracle on 4 threads",
             "frac": None, "parity": bool(parity), "chosen": sig(res_best)}
 
 

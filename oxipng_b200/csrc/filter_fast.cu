@@ -1509,18 +1509,47 @@ __device__ __noinline__ void alpha_rewrite_row(int f, uint8_t *line, const uint8
         if (rgba8) {
             if ((lw[s0] >> 24) != 0) continue;
             if (s0 > 0 && (lw[s0 - 1] >> 24) == 0) continue; // not a run start
+            // end of the run first (independent loads, four at a time), then the recurrence with the pixels above
+            // fetched four ahead: the step-to-step chain is arithmetic only
+            uint32_t e = s0 + 1;
+            while (e + 4 <= npix) {
+                const uint32_t a0 = lw[e] >> 24, a1 = lw[e + 1] >> 24, a2 = lw[e + 2] >> 24, a3 = lw[e + 3] >> 24;
+                if (a0 | a1 | a2 | a3) break;
+                e += 4;
+            }
+            while (e < npix && (lw[e] >> 24) == 0) e++;
             uint32_t left = s0 ? lw[s0 - 1] : 0u, ul = s0 ? pw[s0 - 1] : 0u;
-            for (uint32_t i = s0; i < npix; i++) {
-                if (i > s0 && (lw[i] >> 24) != 0) break;
-                const uint32_t up = pw[i];
-                uint32_t v;
-                if (f == 1) v = i == 0 ? lw[pv0] : left;                              // Sub: colour of the pixel before
-                else if (f == 3) v = i == 0 ? ((up >> 1) & 0x7F7F7F7Fu) : __vhaddu4(left, up); // Average
-                else v = i == 0 ? __vminu4(lw[pv0], up) : paeth4(left, up, ul);               // Paeth
+            uint32_t i = s0;
+            if (i == 0) { // first pixel of the row: mod.rs:126-131,162,173
+                const uint32_t up = pw[0];
+                uint32_t v = f == 1 ? lw[pv0] : f == 3 ? ((up >> 1) & 0x7F7F7F7Fu) : __vminu4(lw[pv0], up);
                 v &= 0x00FFFFFFu;
-                lw[i] = v;
+                lw[0] = v;
                 left = v;
                 ul = up;
+                i = 1;
+            }
+            if (f == 1) { // Sub: the colour of the pixel before the run, all the way
+                const uint32_t v = left & 0x00FFFFFFu;
+                for (; i < e; i++) lw[i] = v;
+            } else {
+                for (; i + 4 <= e; i += 4) {
+                    const uint32_t u0 = pw[i], u1 = pw[i + 1], u2 = pw[i + 2], u3 = pw[i + 3];
+                    const uint32_t v0 = (f == 3 ? __vhaddu4(left, u0) : paeth4(left, u0, ul)) & 0x00FFFFFFu;
+                    const uint32_t v1 = (f == 3 ? __vhaddu4(v0, u1) : paeth4(v0, u1, u0)) & 0x00FFFFFFu;
+                    const uint32_t v2 = (f == 3 ? __vhaddu4(v1, u2) : paeth4(v1, u2, u1)) & 0x00FFFFFFu;
+                    const uint32_t v3 = (f == 3 ? __vhaddu4(v2, u3) : paeth4(v2, u3, u2)) & 0x00FFFFFFu;
+                    lw[i] = v0; lw[i + 1] = v1; lw[i + 2] = v2; lw[i + 3] = v3;
+                    left = v3;
+                    ul = u3;
+                }
+                for (; i < e; i++) {
+                    const uint32_t up = pw[i];
+                    const uint32_t v = (f == 3 ? __vhaddu4(left, up) : paeth4(left, up, ul)) & 0x00FFFFFFu;
+                    lw[i] = v;
+                    left = v;
+                    ul = up;
+                }
             }
         } else {
             uint8_t *px = line + (size_t)s0 * bpp;
@@ -1617,8 +1646,12 @@ __device__ __forceinline__ uint32_t alpha_score(int f, int kind, const uint8_t *
         if (threadIdx.x == 0) acc[0] = 0;
         return sres;
     }
-    // AK_BIGRAM: every window (t[p-1], t[p]), p = 1..len, t[0] = f, into the hash table; distinct keys / sum ilog2i(count)
+    // AK_BIGRAM: every window (t[p-1], t[p]), p = 1..len, t[0] = f.  Windows whose two residuals lie in [-16, 15] are
+    // counted in a dense 32 x 32 table (the first 4 KB of `tab`), the others in the hash table behind it (CAS inserts are
+    // an order of magnitude dearer): disjoint key sets, so distinct keys / sum ilog2i(count) add up exactly.
+    uint32_t *hash = tab + 1024;
     const uint32_t hmask = hslots - 1, hshift = (uint32_t)__clz((int)hslots) + 1;
+    bool any_out = false;
     for (uint32_t c = threadIdx.x; c < ((nchunks + 31u) & ~31u); c += ALPHA_NT) {
         uint32_t r[4] = {0, 0, 0, 0};
         const int valid = (int)len - 16 * (int)c;
@@ -1630,13 +1663,28 @@ __device__ __forceinline__ uint32_t alpha_score(int f, int kind, const uint8_t *
         for (int k = 0; k < 4; k++)
             for (int j = 0; j < 4; j++) {
                 const uint32_t b = (r[k] >> (8 * j)) & 255u;
-                if (4 * k + j < valid) h0_add(tab, (p << 8) | b, hshift, hmask);
+                if (4 * k + j < valid) {
+                    const uint32_t pa = (p + 16u) & 255u, pb = (b + 16u) & 255u;
+                    if (((pa | pb) & 0xE0u) == 0) {
+                        atomicAdd(&tab[pa * 32u + ((pb + 5u * pa) & 31u)], 1u);
+                    } else {
+                        h0_add(hash, (p << 8) | b, hshift, hmask);
+                        any_out = true;
+                    }
+                }
                 p = b;
             }
     }
-    __syncthreads();
+    const bool sweep_hash = __syncthreads_or(any_out) != 0;
     uint32_t d = 0, e = 0;
-    h0_sweep<ALPHA_NT>(tab, hslots, d, e);
+    {
+        uint4 *t4 = reinterpret_cast<uint4 *>(tab) + threadIdx.x; // 1024 counters: one uint4 per thread
+        const uint4 a = *t4;
+        *t4 = make_uint4(0, 0, 0, 0);
+        d += (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0);
+        e += ilog2i_z(a.x) + ilog2i_z(a.y) + ilog2i_z(a.z) + ilog2i_z(a.w);
+    }
+    if (sweep_hash) h0_sweep<ALPHA_NT>(hash, hslots, d, e);
     d = warp_sum(d);
     e = warp_sum(e);
     if (lane == 0 && d) {
@@ -1657,7 +1705,7 @@ __global__ void __launch_bounds__(ALPHA_NT, 4) k_alpha(const __grid_constant__ A
     uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw + 64);            // [2] score accumulators
     uint32_t *sh_first = reinterpret_cast<uint32_t *>(smem_raw + 80);
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw + ALPHA_HDR);
-    const uint32_t tab_bytes = KIND == AK_ENTROPY ? 4096u : KIND == AK_BIGRAM ? P.hslots * 4u : 0u;
+    const uint32_t tab_bytes = KIND == AK_ENTROPY ? 4096u : KIND == AK_BIGRAM ? 4096u + P.hslots * 4u : 0u;
     uint8_t *bufs = smem_raw + ALPHA_HDR + tab_bytes; // ring slot 0, ring slot 1, keep A, keep B
     const int tid = threadIdx.x;
     const uint32_t bpp = P.g.bpp, cb = P.g.color_bytes, shift = 8 * (bpp % 4);
@@ -1833,7 +1881,7 @@ uint32_t alpha_hslots(const Geom &g) {
     return h;
 }
 uint32_t alpha_smem(const Geom &g, int kind) {
-    return ALPHA_HDR + (kind == AK_ENTROPY ? 4096u : kind == AK_BIGRAM ? alpha_hslots(g) * 4u : 0u) + 4u * slot_bytes(g);
+    return ALPHA_HDR + (kind == AK_ENTROPY ? 4096u : kind == AK_BIGRAM ? 4096u + alpha_hslots(g) * 4u : 0u) + 4u * slot_bytes(g);
 }
 
 std::mutex g_occ_mu;

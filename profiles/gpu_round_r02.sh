@@ -1,0 +1,15 @@
+#!/bin/bash
+# One GPU-box visit of round 2: parity tests, the bench line, the ncu launch list of the bench command and full captures of
+# the dominant kernel (c5) and of the other tuned kernels.   gpurun --timeout 1800 -- 'bash profiles/gpu_round_r02.sh [tag]'
+tag=${1:-r02}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/${tag}_pytest.log
+tail -3 gpurun_out/${tag}_pytest.log
+python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench exit $?"
+python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/${tag}_bench_reference.json 2>/dev/null; echo "reference arm exit $?"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${tag}_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-check --no-others --images-per-gpu 64 > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu list exit $?"
+for cfg in c5 c3a c1 c2; do
+  ncu --set full --clock-control none --import-source on -k regex:k_fast -s 2 -c 1 -o gpurun_out/${tag}_${cfg}_full -f \
+      python profiles/run_config.py $cfg --images 64 --iters 3 > gpurun_out/${tag}_ncu_${cfg}.log 2>&1; echo "ncu $cfg exit $?"
+done

@@ -1,0 +1,76 @@
+"""Renders the measured tables of DESIGN.md section 8 and README.md from the bench lines in profiles/.
+
+    python profiles/make_tables.py profiles/bench_r02_n1.json [profiles/bench_r02_n2.json ...] > /tmp/tables.md
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+r1 = json.load(open(os.path.join(HERE, "bench_r01_n1.json")))
+d = json.load(open(sys.argv[1]))
+more = [json.load(open(p)) for p in sys.argv[2:]]
+oc, r1oc = d["other_configs"], r1.get("other_configs", {})
+
+
+def pct(x):
+    return "–" if x is None else f"{100 * x:.1f} %"
+
+
+def r1_of(name):
+    m = {"c1_minsum_rgba8_4096": "c1_minsum_rgba8_4096", "c2_entropy_rgb8_8192": "c2_entropy_rgb8_8192",
+         "c2_basic_paeth_rgb8_8192": "c2_basic_paeth_rgb8_8192", "c2_basic_none_rgb8_8192": "c2_basic_none_rgb8_8192",
+         "c3a_bigrams_rgba16_4096": "c3a_bigrams_rgba16_4096", "c3a_bigent_rgba16_4096": "c3a_bigent_rgba16_4096",
+         "c3b_bigrams_bigent_rgba8_4096_adam7": "c3b_bigrams_bigent_rgba8_4096_adam7",
+         "bigrams_bigent_rgba8_4096": "bigrams_bigent_rgba8_4096"}.get(name)
+    v = r1oc.get(m) if m else None
+    return f"{v['ms']:.4f} ms / {pct(v['frac_of_measured_hbm'])}" if v else "–"
+
+
+out = []
+out.append("| Config | time | raw pixels | of HBM roofline | parity | r1 (time / roofline) |")
+out.append("|---|---|---|---|---|---|")
+out.append(f"| **c5: 1250 × 1024² RGBA8, {{None,Bigrams,BigEnt}} fused** (`value`) | **{d['ms_per_step']:.2f} ms** | "
+           f"**{d['value']:.1f} GB/s, {d['images_per_s'] / 1e3:.1f} k images/s** | **{pct(d['roofline']['frac'])}** | spot check ok | "
+           f"{r1['ms_per_step']:.2f} ms / {pct(r1['roofline']['frac'])} |")
+for k, v in oc.items():
+    if not isinstance(v, dict) or "ms" not in v or "frac" not in v or k.startswith("o2_flow"):
+        continue
+    raw = f"{v['raw_pixel_GBps']:.0f} GB/s" + (f", {v['images_per_s'] / 1e3:.1f} k images/s" if "images_per_s" in v else "")
+    out.append(f"| `{k}`{' (' + v['tier'] + ' tier)' if v.get('tier') else ''} | {v['ms']:.4f} ms | {raw} | {pct(v['frac'])} | {v['parity']} | {r1_of(k)} |")
+out.append("")
+c4 = oc.get("c4_reductions_2048_256colours", {})
+if c4:
+    out.append("Reduction scans (c4: 2048² images with ≤ 256 colours). `device` = CUDA events around the resident call (its kernels, "
+               "the stream-ordered allocation and the few-byte state read-back); `resident` = wall time of the handle → handle call; "
+               "`host buffers` = the same entry point with pageable host memory (upload + download inside):")
+    out.append("")
+    out.append("| Entry point | device | resident call | host buffers | parity |")
+    out.append("|---|---|---|---|---|")
+    for k, v in c4.items():
+        out.append(f"| `{k}` | {v['ms'] * 1e3:.0f} µs | {v['resident_call_ms'] * 1e3:.0f} µs | {v['host_call_ms']:.2f} ms | {v['parity']} |")
+    out.append("")
+fl = oc.get("o2_flow_resident_2048_256colours")
+if fl:
+    out.append(f"`-o2` reduction stage on one 2048² RGBA8 image with 256 colours (lib.rs:385-420; {fl['candidates']} candidates, evaluator set "
+               f"{{None, Bigrams}}): reductions **{fl['resident_reductions_ms']:.2f} ms resident** (one upload, every scan on the device) vs "
+               f"{fl['host_buffer_reductions_ms']:.1f} ms through host buffers vs {fl['cpu_oracle_reductions_ms']:.0f} ms for the CPU oracle; "
+               f"whole stage incl. the evaluator's host-side zlib: {fl['resident_total_ms']:.0f} / {fl['host_buffer_total_ms']:.0f} / "
+               f"{fl['cpu_oracle_flow_ms']:.0f} ms; same candidates, same winner: {fl['parity']}.")
+    out.append("")
+e, ep, cc = d["e2e"], d.get("e2e_pageable"), d.get("copy_ceiling")
+cpu = d.get("cpu_baseline") or {}
+out.append(f"End to end (`e2e`, `oxi_filter_batch`, H2D {e['h2d_bytes_per_step'] / 1e9:.2f} GB + D2H {e['d2h_bytes_per_step'] / 1e9:.2f} GB per step inside "
+           f"the timed region): **{e['value']:.1f} GB/s** raw pixels with pinned buffers"
+           + (f" = {100 * cc['e2e_fraction_of_copy_ceiling']:.0f} % of the copy ceiling ({cc['per_rank_GBps']:.1f} GB/s of PCIe traffic both ways)" if cc and 'e2e_fraction_of_copy_ceiling' in cc else "")
+           + (f"; **{ep['value']:.1f} GB/s** with pageable buffers (r1: 3.65 measured the same way)" if ep and 'value' in ep else "")
+           + (f". CPU baseline beside it ({cpu.get('kind')}, {cpu.get('cores')} threads): {cpu.get('value', 0):.2f} GB/s." if cpu else "."))
+out.append("")
+rows = [d] + more
+out.append("| GPUs | value (GB/s raw) | ms per step | e2e (GB/s raw) | copy ceiling (GB/s raw) | row band MinSum 16384² | row band Bigrams 16384² |")
+out.append("|---|---|---|---|---|---|---|")
+for x in rows:
+    rb, c = x.get("row_band") or {}, x.get("copy_ceiling") or {}
+    out.append(f"| {x['n_gpus']} | {x['value']:.1f} | {x['ms_per_step']:.2f} | {x['e2e']['value']:.1f} | {c.get('raw_pixel_GBps_if_copy_bound', 0):.1f} | "
+               f"{rb.get('minsum', {}).get('ms', 0):.1f} ms | {rb.get('bigrams', {}).get('ms', 0):.1f} ms |")
+print("\n".join(out))

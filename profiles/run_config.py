@@ -36,6 +36,9 @@ cfg = {
     "c5n6": (1024, 1024, 4, 8, [S.NONE, S.Bigrams, S.BigEnt], a.images),
     "c5n12": (1024, 1024, 4, 8, [S.NONE, S.Bigrams, S.BigEnt], a.images),
     "c5n24": (1024, 1024, 4, 8, [S.NONE, S.Bigrams, S.BigEnt], a.images),
+    "o2": (1024, 1024, 4, 8, [S.NONE, S.SUB, S.Entropy, S.Bigrams], a.images),
+    "alpha": (1024, 1024, 4, 8, [S.MinSum], a.images),          # optimize_alpha on, 10 % of the 16x16 blocks transparent
+    "alphao2": (1024, 1024, 4, 8, [S.NONE, S.SUB, S.Entropy, S.Bigrams], a.images),
 }[a.config]
 w, h, ch, bd, strat, n = cfg
 if n == 1:
@@ -53,6 +56,14 @@ if a.config.startswith("c5n"):  # photo + extra uniform noise in [-A, A] on the 
     nz = torch.randint(-A, A + 1, d.shape, dtype=torch.int16, device=dev)
     nz[3::4] = 0
     d = ((d.to(torch.int16) + nz) & 255).to(torch.uint8)
+alpha = a.config.startswith("alpha")
+if alpha:
+    g = torch.Generator(device=dev); g.manual_seed(9)
+    v = d.view(n, h, w, 4)
+    m = (torch.rand((n, h // 16, w // 16), device=dev, generator=g) < 0.10).repeat_interleave(16, 1).repeat_interleave(16, 2)
+    rnd = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=dev, generator=g)
+    v[..., :3] = torch.where(m[..., None], rnd, v[..., :3])
+    v[..., 3] = torch.where(m, torch.zeros_like(v[..., 3]), v[..., 3])
 if interlaced:
     # the same image in the Adam7 layout (oxi_interlace_image, interlace.rs:6-60): every pass is a subsampled picture
     prog = ox.PngImage(ox.IhdrData(w, h, ct, ox.BitDepth(bd), False), d.cpu().numpy())
@@ -66,7 +77,7 @@ ms = []
 for i in range(a.iters):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
-    ox.filter_batch_device(0, st.cuda_stream, hdr, d.data_ptr(), per, n, strat, False, [t.data_ptr() for t in o],
+    ox.filter_batch_device(0, st.cuda_stream, hdr, d.data_ptr(), per, n, strat, alpha, [t.data_ptr() for t in o],
                            [t.data_ptr() for t in u])
     e1.record(st)
     torch.cuda.synchronize()
