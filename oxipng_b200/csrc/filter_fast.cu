@@ -36,7 +36,7 @@ constexpr int HALF_NT = 256, HALF_OCC = 4;
 // are spread wider than +-16 (film grain, dithering): 512-thread CTAs, two resident per SM
 constexpr int SC_WIDE = 16;
 __host__ __device__ constexpr int rb_of(int sc) { return (sc & SC_WIDE) ? 6 : 5; } // bits of a range code
-constexpr int HIST_REP = 4;      // copies of each Entropy histogram (lane & 3) to thin same-address atomics
+constexpr int HIST_REP = 1;      // copies of each Entropy histogram: one (lanes on the same bin are merged by ATOMS.POPC.INC)
 constexpr uint32_t PAD = 32;     // zero bytes in front of every staged row (left/upleft of the first pixel)
 constexpr uint32_t SMEM_HDR = 1024;
 constexpr uint32_t SCORE_WORDS = 40;   // s_min/s_ent/s_bgc/s_bge/s_out, 8 words each; three sets rotate row by row
@@ -321,67 +321,64 @@ __device__ __forceinline__ void minsum_pass(const uint8_t *cur, const uint8_t *u
 }
 
 // Entropy: histogram the residual bytes of all five filters (filter-type byte added at scoring time).  The counter of
-// byte value v of filter f in the lane's replica rep sits at byte offset f*4096 + rep*1024 + (v ^ 8*rep)*4 (the
-// rotation spreads the replicas of one hot value over the banks): low byte (v & 63) << 2, high byte v >> 6 | rep << 2,
-// composed per window by one prmt out of two pre-scaled words; f*4096 is an immediate of the atomic.
-__device__ __forceinline__ void hist_word(uint32_t hist_base, uint32_t r, uint32_t rotw, uint32_t crep) {
-    const uint32_t rx = r ^ rotw;
-    const uint32_t lo = (rx * 4u) & 0xFCFCFCFCu, hi = ((rx >> 6) & 0x03030303u) | crep;
-    smem_inc(hist_base + prmt(lo, hi, 0xCC40u));
-    smem_inc(hist_base + prmt(lo, hi, 0xDD51u));
-    smem_inc(hist_base + prmt(lo, hi, 0xEE62u));
-    smem_inc(hist_base + prmt(lo, hi, 0xFF73u));
+// byte value v of filter f sits at byte offset f*1024 + v*4: low byte (v & 63) << 2, high byte v >> 6, composed per byte by
+// one prmt out of two pre-scaled words; the histogram's shared-window address (+ f*1024) is an immediate of the atomic.
+// One copy per histogram: round 1 kept four lane-selected, bank-rotated replicas (2.2 wavefronts per ATOMS measured);
+// replaying the lane -> byte map on the c2 image gives 2.14 for that layout and 1.2 for a single copy, because the lanes
+// of one instruction that hold the same residual value then hit the same counter and are merged by the hardware.
+constexpr uint32_t HIST_ADDR = SMEM_WIN + SMEM_HDR; // the histograms are the first thing behind the header in every layout
+template <uint32_t HB>
+__device__ __forceinline__ void hist_word(uint32_t r) {
+    const uint32_t lo = (r * 4u) & 0xFCFCFCFCu, hi = (r >> 6) & 0x03030303u;
+    smem_inc_at<HB>(prmt(lo, hi, 0xCC40u));
+    smem_inc_at<HB>(prmt(lo, hi, 0xDD51u));
+    smem_inc_at<HB>(prmt(lo, hi, 0xEE62u));
+    smem_inc_at<HB>(prmt(lo, hi, 0xFF73u));
 }
-__device__ __forceinline__ void hist_word_tail(uint32_t hist_base, uint32_t r, uint32_t rep, int nvalid) {
-    for (int j = 0; j < nvalid; j++) smem_inc(hist_base + rep * 1024u + ((((r >> (8 * j)) & 255u) ^ (8u * rep)) << 2));
+template <uint32_t HB>
+__device__ __forceinline__ void hist_word_tail(uint32_t r, int nvalid) {
+    for (int j = 0; j < nvalid; j++) smem_inc(HB + (((r >> (8 * j)) & 255u) << 2));
 }
 template <int D, bool TAIL>
-__device__ __forceinline__ void entropy_chunk(const uint8_t *cur, const uint8_t *up, uint32_t c, int valid, uint32_t shift,
-                                              uint32_t hist_base, uint32_t rep) {
+__device__ __forceinline__ void entropy_chunk(const uint8_t *cur, const uint8_t *up, uint32_t c, int valid, uint32_t shift) {
     const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
-    const uint32_t rotw = rep * 0x08080808u, crep = rep * 0x04040404u;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t x = cw.w[k + 2], u = uw.w[k + 2], l = left_word<D>(cw, k, shift), ul = left_word<D>(uw, k, shift);
         const uint32_t r1 = __vsub4(x, l), r2 = __vsub4(x, u), r3 = __vsub4(x, __vhaddu4(l, u)), r4 = __vsub4(x, paeth4(l, u, ul));
         if (!TAIL) {
-            hist_word(hist_base + 0 * 4096u, x, rotw, crep);
-            hist_word(hist_base + 1 * 4096u, r1, rotw, crep);
-            hist_word(hist_base + 2 * 4096u, r2, rotw, crep);
-            hist_word(hist_base + 3 * 4096u, r3, rotw, crep);
-            hist_word(hist_base + 4 * 4096u, r4, rotw, crep);
+            hist_word<HIST_ADDR + 0 * 1024u>(x);
+            hist_word<HIST_ADDR + 1 * 1024u>(r1);
+            hist_word<HIST_ADDR + 2 * 1024u>(r2);
+            hist_word<HIST_ADDR + 3 * 1024u>(r3);
+            hist_word<HIST_ADDR + 4 * 1024u>(r4);
         } else {
             const int nv = min(valid - 4 * k, 4);
             if (nv <= 0) break;
-            hist_word_tail(hist_base + 0 * 4096u, x, rep, nv);
-            hist_word_tail(hist_base + 1 * 4096u, r1, rep, nv);
-            hist_word_tail(hist_base + 2 * 4096u, r2, rep, nv);
-            hist_word_tail(hist_base + 3 * 4096u, r3, rep, nv);
-            hist_word_tail(hist_base + 4 * 4096u, r4, rep, nv);
+            hist_word_tail<HIST_ADDR + 0 * 1024u>(x, nv);
+            hist_word_tail<HIST_ADDR + 1 * 1024u>(r1, nv);
+            hist_word_tail<HIST_ADDR + 2 * 1024u>(r2, nv);
+            hist_word_tail<HIST_ADDR + 3 * 1024u>(r3, nv);
+            hist_word_tail<HIST_ADDR + 4 * 1024u>(r4, nv);
         }
     }
 }
 template <int D, int NT>
 __device__ __forceinline__ void entropy_pass(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
                                              uint32_t *hist) {
-    static_assert(HIST_REP == 4, "replica select and rotation are written for four replicas");
-    const uint32_t nfull = len >> 4, rep = threadIdx.x & (HIST_REP - 1), hist_base = smem_u32(hist);
-    for (uint32_t c = threadIdx.x; c < nfull; c += NT) entropy_chunk<D, false>(cur, up, c, 16, shift, hist_base, rep);
-    if ((len & 15u) && threadIdx.x == (nfull % NT)) entropy_chunk<D, true>(cur, up, nfull, (int)(len & 15u), shift, hist_base, rep);
+    static_assert(HIST_REP == 1, "the histogram addressing is written for one copy");
+    const uint32_t nfull = len >> 4;
+    for (uint32_t c = threadIdx.x; c < nfull; c += NT) entropy_chunk<D, false>(cur, up, c, 16, shift);
+    if ((len & 15u) && threadIdx.x == (nfull % NT)) entropy_chunk<D, true>(cur, up, nfull, (int)(len & 15u), shift);
 }
 // sum over present values of ilog2i(count) (strategies.rs:136-142); clears the histograms for the next row.
 template <int NT>
 __device__ __forceinline__ void entropy_score(uint32_t *hist, uint32_t *s_ent) {
     for (uint32_t idx = threadIdx.x; idx < 5 * 256; idx += NT) {
         const uint32_t f = idx >> 8, v = idx & 255u;
-        uint32_t *h = hist + f * HIST_REP * 256;
-        uint32_t cnt = (v == f) ? 1u : 0u; // the filter-type byte that leads the filtered line
-#pragma unroll
-        for (int r = 0; r < HIST_REP; r++) { // replica r keeps bin v at v ^ 8r
-            cnt += h[r * 256 + (v ^ (uint32_t)(8 * r))];
-            h[r * 256 + (v ^ (uint32_t)(8 * r))] = 0;
-        }
-        uint32_t s = warp_sum(cnt ? ilog2i(cnt) : 0u);
+        const uint32_t cnt = hist[idx] + ((v == f) ? 1u : 0u); // + the filter-type byte that leads the filtered line
+        hist[idx] = 0;
+        uint32_t s = warp_sum(ilog2i(cnt | (cnt == 0)) * (cnt != 0));
         if ((threadIdx.x & 31) == 0) atomicAdd(&s_ent[f], s);
     }
 }
@@ -1601,7 +1598,8 @@ __device__ __forceinline__ void alpha_residual_chunk(int f, const uint8_t *cur, 
 // MinSum / Bigrams: lower is better; Entropy / BigEnt: higher is better as i32 (strategies.rs:95,143,189,221).
 template <int D, int KIND>
 __device__ __forceinline__ uint32_t alpha_score(int f, int kind, const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
-                                                uint32_t *tab, uint32_t hslots, uint32_t *acc /* [2], zero on entry */) {
+                                                uint32_t *tab, uint32_t hslots, uint32_t *acc /* [2], zero on entry */,
+                                                bool coarse = false /* AK_BIGRAM: keys merged to their low five bits */) {
     const uint32_t nchunks = (len + 15) >> 4, lane = threadIdx.x & 31u;
     if (KIND == AK_MINSUM) {
         uint32_t a = 0; // sum over bytes of ||r| - 128| (see minsum_chunk); bytes past the row give 128 each
@@ -1664,7 +1662,7 @@ __device__ __forceinline__ uint32_t alpha_score(int f, int kind, const uint8_t *
             for (int j = 0; j < 4; j++) {
                 const uint32_t b = (r[k] >> (8 * j)) & 255u;
                 if (4 * k + j < valid) {
-                    const uint32_t pa = (p + 16u) & 255u, pb = (b + 16u) & 255u;
+                    const uint32_t pa = coarse ? (p & 31u) : ((p + 16u) & 255u), pb = coarse ? (b & 31u) : ((b + 16u) & 255u);
                     if (((pa | pb) & 0xE0u) == 0) {
                         atomicAdd(&tab[pa * 32u + ((pb + 5u * pa) & 31u)], 1u);
                     } else {
@@ -1781,13 +1779,26 @@ __global__ void __launch_bounds__(ALPHA_NT, 4) k_alpha(const __grid_constant__ A
                     for (uint32_t c = tid; c < (len + 15) / 16; c += ALPHA_NT) { const uint4 v = c4[c]; nz |= v.x | v.y | v.z | v.w; }
                     if (__syncthreads_or(nz != 0)) {
                         uint32_t best = 0;
+                        // Bigrams / BigEnt: trial 0 (the raw bytes: every window would take the hash path) is first scored
+                        // on coarse keys, which bounds its score from the losing side (see bigram_row_small); its exact
+                        // score is computed -- from the copy kept in keep_best -- only if a later trial does not beat the
+                        // bound while None is still the best
+                        bool best_is_bound = false;
+                        const bool lower = st.kind == OXI_MINSUM || st.kind == OXI_BIGRAMS;
                         for (int f = 0; f < 5; f++) { // RowFilter::ALL order, cumulative rewriting of the one line
                             alpha_rewrite_row(f, w, keep_prev, len, bpp, cb, sh_first);
-                            const uint32_t sres = alpha_score<D, KIND>(f, st.kind, w, keep_prev, len, shift, tab, P.hslots, acc);
-                            const bool lower = st.kind == OXI_MINSUM || st.kind == OXI_BIGRAMS;
-                            if (f == 0 || (lower ? sres < best : (int32_t)sres > (int32_t)best)) {
+                            const bool coarse0 = KIND == AK_BIGRAM && f == 0;
+                            const uint32_t sres = alpha_score<D, KIND>(f, st.kind, w, keep_prev, len, shift, tab, P.hslots, acc, coarse0);
+                            bool wins = f == 0 || (lower ? sres < best : (int32_t)sres > (int32_t)best);
+                            if (KIND == AK_BIGRAM && f > 0 && !wins && best_is_bound) {
+                                best = alpha_score<D, KIND>(0, st.kind, keep_best, keep_prev, len, shift, tab, P.hslots, acc, false);
+                                best_is_bound = false;
+                                wins = lower ? sres < best : (int32_t)sres > (int32_t)best;
+                            }
+                            if (wins) {
                                 best = sres;
                                 best_f = f;
+                                best_is_bound = coarse0;
                                 if (f < 4) { // keep the line as this trial left it (the last trial's line is `w` itself)
                                     const uint4 *s4 = reinterpret_cast<const uint4 *>(w);
                                     uint4 *d4 = reinterpret_cast<uint4 *>(keep_best);

@@ -9,7 +9,13 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_o
 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/${tag}_bench_reference.json 2>/dev/null; echo "reference arm exit $?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-check --no-others --images-per-gpu 64 > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu list exit $?"
-for cfg in c5 c3a c1 c2; do
-  ncu --set full --clock-control none --import-source on -k regex:k_fast -s 2 -c 1 -o gpurun_out/${tag}_${cfg}_full -f \
+for cfg in c5 c3a c1 c2 o2 alpha; do
+  ncu --set full --clock-control none --import-source on -k regex:"k_fast|k_alpha" -s 2 -c 1 -o gpurun_out/${tag}_${cfg}_full -f \
       python profiles/run_config.py $cfg --images 64 --iters 3 > gpurun_out/${tag}_ncu_${cfg}.log 2>&1; echo "ncu $cfg exit $?"
+  # text summaries are made here: gpurun copies back at most 64 MiB, and a full capture is ~17 MB
+  python profiles/summarize_ncu.py gpurun_out/${tag}_${cfg}_full.ncu-rep > gpurun_out/${tag}_${cfg}_ncu.txt 2>&1
+  python profiles/hot_sass.py gpurun_out/${tag}_${cfg}_full.ncu-rep 30 >> gpurun_out/${tag}_${cfg}_ncu.txt 2>&1
+  if [ "$cfg" != "c5" ]; then rm -f gpurun_out/${tag}_${cfg}_full.ncu-rep; fi
 done
+python profiles/line_profile.py gpurun_out/${tag}_c5_full.ncu-rep oxipng_b200/liboxipng_b200.so k_fastILi1ELi12E 60 > gpurun_out/${tag}_c5_line_profile.txt 2>&1
+python profiles/launch_list.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_launch_list.txt 2>&1
