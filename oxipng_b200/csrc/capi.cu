@@ -418,6 +418,7 @@ int filter_host_chunk(DeviceCtx *c, Slot *slot, const Geom &g, const uint8_t *da
 int filter_resident(int device, cudaStream_t stream, const oxi_ihdr *h, const uint8_t *d_data, size_t data_len, size_t n_images,
                     const oxi_strategy *strategies, size_t k, int optimize_alpha, uint8_t *const *d_outs,
                     uint8_t *const *d_filters_used, unsigned flags) {
+    Trace trace("oxi_filter (resident)");
     Geom g;
     if (!build_geom(h, data_len, optimize_alpha, &g)) return fail(OXI_E_ARG, "invalid IHDR");
     if (g.data_len != data_len) return fail(OXI_E_ARG, "data_len is not a whole number of scanlines for this IHDR");
@@ -641,6 +642,7 @@ int oxi_filter_batch_device(int device, void *stream, const oxi_ihdr *h, const u
 int oxi_filter_batch(const oxi_ihdr *h, const uint8_t *data, size_t data_len, size_t n_images,
                      const oxi_strategy *strategies, size_t k, int optimize_alpha, uint8_t *const *outs,
                      uint8_t *const *filters_used, unsigned flags) {
+    Trace trace("oxi_filter_batch (host buffers)");
     Geom g;
     if (!build_geom(h, data_len, optimize_alpha, &g)) return fail(OXI_E_ARG, "invalid IHDR");
     if (!data || !strategies || k == 0 || k > (size_t)MAX_STRATEGIES) return fail(OXI_E_ARG, "bad arguments");
@@ -700,6 +702,7 @@ int oxi_filter_batch(const oxi_ihdr *h, const uint8_t *data, size_t data_len, si
 int oxi_filter_image_sharded(const oxi_ihdr *h, const uint8_t *data, size_t data_len, const oxi_strategy *strategies, size_t k,
                              int optimize_alpha, const int *devices, int n_devices, int bands_per_device, uint8_t *const *outs,
                              uint8_t *const *filters_used, unsigned flags) {
+    Trace trace("oxi_filter_image_sharded");
     Geom g;
     if (!build_geom(h, data_len, optimize_alpha, &g)) return fail(OXI_E_ARG, "invalid IHDR");
     if (!data || !strategies || k == 0 || k > (size_t)MAX_STRATEGIES || !devices || n_devices < 1 || n_devices > 64)

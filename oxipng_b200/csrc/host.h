@@ -5,9 +5,17 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: ranges show up in Nsight Systems / ncu timelines, no-ops otherwise
+
 #include "common.cuh"
 
 namespace oxi {
+
+// NVTX range around one C-ABI call (tracing)
+struct Trace {
+    explicit Trace(const char *name) { nvtxRangePushA(name); }
+    ~Trace() { nvtxRangePop(); }
+};
 
 int fail(int code, const char *msg);
 int fail_cuda(cudaError_t e, const char *where);

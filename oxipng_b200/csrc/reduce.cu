@@ -718,6 +718,7 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
 // ---- host-side call scaffolding -------------------------------------------------------------------------------------------
 
 struct Call {
+    Trace trace{"oxi reduction scan"};
     DeviceCtx *c = nullptr;
     Slot *s = nullptr;
     cudaStream_t stream = nullptr; // the slot's own stream, or the caller's in device-resident mode
