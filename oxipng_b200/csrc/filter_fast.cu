@@ -1433,6 +1433,9 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_WIDE) ? 2 : (SC & SC
             sc_ = sn;
             sn = sn + 1 == NS ? 0 : sn + 1;
         }
+        // rows loaded cooperatively were written through the generic proxy; the next band may refill the same slots by TMA
+        // (async proxy): order the two before the barrier that ends the band
+        if (!tma) fence_proxy_async();
         if (!row_end_barrier) __syncthreads(); // the next band's prologue rewrites slots 0 and 1
     }
 }

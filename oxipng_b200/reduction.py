@@ -101,7 +101,9 @@ def reduced_bit_depth_8_or_less(png: PngImage) -> Optional[PngImage]:  # bit_dep
 
 
 def expanded_bit_depth_to_8(png: PngImage) -> Optional[PngImage]:  # bit_depth.rs:170
-    return _with_aux("oxi_expanded_bit_depth_to_8", png, png.ihdr.width * png.ihdr.height)
+    # one output byte per pixel; sized from the data (<= 8 pixels per input byte), not from the IHDR: a non-interlaced
+    # image keeps yielding rows while bytes remain (scan_lines.rs), so the data may hold more rows than ihdr.height
+    return _with_aux("oxi_expanded_bit_depth_to_8", png, max(png.ihdr.width * png.ihdr.height, png.data.size * 8))
 
 
 def reduced_to_indexed(png: PngImage, allow_grayscale: bool) -> Optional[PngImage]:  # color.rs:38
