@@ -1493,18 +1493,20 @@ __device__ __noinline__ void alpha_rewrite_row(int f, uint8_t *line, const uint8
         __syncthreads();
         return;
     }
-    // first non-transparent pixel (only matters when pixel 0 is transparent), mod.rs:126-131
-    if (tid == 0) *sh_first = 0xFFFFFFFFu;
-    __syncthreads();
+    // first non-transparent pixel (only matters when pixel 0 is transparent -- a uniform condition), mod.rs:126-131
+    uint32_t pv0 = 0;
     if (npix && px_clear(line, cb, bpp)) {
+        if (tid == 0) *sh_first = 0xFFFFFFFFu;
+        __syncthreads();
         uint32_t mine = 0xFFFFFFFFu;
         for (uint32_t i = tid; i < npix; i += ALPHA_NT)
             if (!px_clear(line + (size_t)i * bpp, cb, bpp)) { mine = i; break; }
         if (mine != 0xFFFFFFFFu) atomicMin(sh_first, mine);
+        __syncthreads();
+        const uint32_t first_opaque = *sh_first; // 0xFFFFFFFF: none -> prev = i (= 0)
+        pv0 = first_opaque == 0xFFFFFFFFu ? 0u : first_opaque;
+        __syncthreads(); // (sh_first is rewritten by the next trial)
     }
-    __syncthreads();
-    const uint32_t first_opaque = *sh_first; // 0xFFFFFFFF: none -> prev = i (= 0)
-    const uint32_t pv0 = first_opaque == 0xFFFFFFFFu ? 0u : first_opaque;
     for (uint32_t s0 = tid; s0 < npix; s0 += ALPHA_NT) {
         if (rgba8) {
             if ((lw[s0] >> 24) != 0) continue;
@@ -1601,7 +1603,7 @@ __device__ __forceinline__ void alpha_residual_chunk(int f, const uint8_t *cur, 
 // MinSum / Bigrams: lower is better; Entropy / BigEnt: higher is better as i32 (strategies.rs:95,143,189,221).
 template <int D, int KIND>
 __device__ __forceinline__ uint32_t alpha_score(int f, int kind, const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
-                                                uint32_t *tab, uint32_t hslots, uint32_t *acc /* [2], zero on entry */,
+                                                uint32_t *tab, uint32_t hslots, uint32_t *acc /* [2], this call's own, zero on entry */,
                                                 bool coarse = false /* AK_BIGRAM: keys merged to their low five bits */) {
     const uint32_t nchunks = (len + 15) >> 4, lane = threadIdx.x & 31u;
     if (KIND == AK_MINSUM) {
@@ -1615,10 +1617,7 @@ __device__ __forceinline__ uint32_t alpha_score(int f, int kind, const uint8_t *
         a = warp_sum(a);
         if (lane == 0 && a) atomicAdd(&acc[0], a);
         __syncthreads();
-        const uint32_t sres = 128u * 16u * nchunks - acc[0] + (uint32_t)f; // + |f| of the filter-type byte
-        __syncthreads();
-        if (threadIdx.x == 0) acc[0] = 0;
-        return sres;
+        return 128u * 16u * nchunks - acc[0] + (uint32_t)f; // + |f| of the filter-type byte
     }
     if (KIND == AK_ENTROPY) {
         const uint32_t rep = threadIdx.x & 3u;
@@ -1642,10 +1641,7 @@ __device__ __forceinline__ uint32_t alpha_score(int f, int kind, const uint8_t *
         e = warp_sum(e);
         if (lane == 0 && e) atomicAdd(&acc[0], e);
         __syncthreads();
-        const uint32_t sres = acc[0];
-        __syncthreads();
-        if (threadIdx.x == 0) acc[0] = 0;
-        return sres;
+        return acc[0];
     }
     // AK_BIGRAM: every window (t[p-1], t[p]), p = 1..len, t[0] = f.  Windows whose two residuals lie in [-16, 15] are
     // counted in a dense 32 x 32 table (the first 4 KB of `tab`), the others in the hash table behind it (CAS inserts are
@@ -1693,18 +1689,15 @@ __device__ __forceinline__ uint32_t alpha_score(int f, int kind, const uint8_t *
         atomicAdd(&acc[1], e);
     }
     __syncthreads();
-    const uint32_t sres = kind == OXI_BIGRAMS ? acc[0] : acc[1];
-    __syncthreads();
-    if (threadIdx.x == 0) acc[0] = acc[1] = 0;
-    return sres;
+    return kind == OXI_BIGRAMS ? acc[0] : acc[1];
 }
 
 template <int D, int KIND>
 __global__ void __launch_bounds__(ALPHA_NT, 4) k_alpha(const __grid_constant__ AlphaParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);                 // 2 mbarriers
-    uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw + 64);            // [2] score accumulators
-    uint32_t *sh_first = reinterpret_cast<uint32_t *>(smem_raw + 80);
+    uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw + 64);            // [6][2] score accumulators: one pair per scoring call of a row
+    uint32_t *sh_first = reinterpret_cast<uint32_t *>(smem_raw + 128);
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw + ALPHA_HDR);
     const uint32_t tab_bytes = KIND == AK_ENTROPY ? 4096u : KIND == AK_BIGRAM ? 4096u + P.hslots * 4u : 0u;
     uint8_t *bufs = smem_raw + ALPHA_HDR + tab_bytes; // ring slot 0, ring slot 1, keep A, keep B
@@ -1714,8 +1707,8 @@ __global__ void __launch_bounds__(ALPHA_NT, 4) k_alpha(const __grid_constant__ A
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        acc[0] = acc[1] = 0;
     }
+    if (tid < 12) acc[tid] = 0;
     for (uint32_t i = tid; i < (tab_bytes + 4u * P.rb) / 4; i += ALPHA_NT) reinterpret_cast<uint32_t *>(smem_raw + ALPHA_HDR)[i] = 0;
     __syncthreads();
     uint32_t parity = 0;
@@ -1780,6 +1773,7 @@ __global__ void __launch_bounds__(ALPHA_NT, 4) k_alpha(const __grid_constant__ A
                     uint32_t nz = 0;
                     const uint4 *c4 = reinterpret_cast<const uint4 *>(w);
                     for (uint32_t c = tid; c < (len + 15) / 16; c += ALPHA_NT) { const uint4 v = c4[c]; nz |= v.x | v.y | v.z | v.w; }
+                    if (tid < 12) acc[tid] = 0; // (the previous row's last reader is behind that row's final barrier)
                     if (__syncthreads_or(nz != 0)) {
                         uint32_t best = 0;
                         // Bigrams / BigEnt: trial 0 (the raw bytes: every window would take the hash path) is first scored
@@ -1791,10 +1785,10 @@ __global__ void __launch_bounds__(ALPHA_NT, 4) k_alpha(const __grid_constant__ A
                         for (int f = 0; f < 5; f++) { // RowFilter::ALL order, cumulative rewriting of the one line
                             alpha_rewrite_row(f, w, keep_prev, len, bpp, cb, sh_first);
                             const bool coarse0 = KIND == AK_BIGRAM && f == 0;
-                            const uint32_t sres = alpha_score<D, KIND>(f, st.kind, w, keep_prev, len, shift, tab, P.hslots, acc, coarse0);
+                            const uint32_t sres = alpha_score<D, KIND>(f, st.kind, w, keep_prev, len, shift, tab, P.hslots, acc + 2 * f, coarse0);
                             bool wins = f == 0 || (lower ? sres < best : (int32_t)sres > (int32_t)best);
                             if (KIND == AK_BIGRAM && f > 0 && !wins && best_is_bound) {
-                                best = alpha_score<D, KIND>(0, st.kind, keep_best, keep_prev, len, shift, tab, P.hslots, acc, false);
+                                best = alpha_score<D, KIND>(0, st.kind, keep_best, keep_prev, len, shift, tab, P.hslots, acc + 10, false);
                                 best_is_bound = false;
                                 wins = lower ? sres < best : (int32_t)sres > (int32_t)best;
                             }
