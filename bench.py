@@ -215,6 +215,16 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        # one disjoint set of host cores per rank: the e2e leg's copy-issuing thread (and the pageable path's copy threads)
+        # of different ranks do not migrate onto each other's cores
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(len(cores) // world, 1)
+            mine = cores[local * per:(local + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+        except OSError:
+            pass
     if world > 1:
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=dev)
