@@ -102,8 +102,10 @@ int oxi_filter_image_multi(const oxi_ihdr *, const uint8_t *data, size_t data_le
                            size_t k, int optimize_alpha, uint8_t *const *outs, uint8_t *const *filters_used);
 
 /* n_images images of identical IHDR, contiguous (image i at data + i*data_len); outs[j] receives
- * n_images * (data_len + rows) bytes, filters_used[j] n_images * rows bytes.  Host buffers (pinned memory
- * recommended); uploads, kernels and downloads are pipelined over chunks of the batch. */
+ * n_images * (data_len + rows) bytes, filters_used[j] n_images * rows bytes.  Host buffers: pinned memory is used in
+ * place; ordinary pageable memory is staged through the library's own pinned buffers by several copy threads.  Uploads,
+ * kernels and downloads are pipelined over chunks of the batch.  For n_images > 1, data_len must be exactly the
+ * scanlines of one image (OXI_E_ARG otherwise). */
 int oxi_filter_batch(const oxi_ihdr *, const uint8_t *data, size_t data_len, size_t n_images,
                      const oxi_strategy *strategies, size_t k, int optimize_alpha, uint8_t *const *outs,
                      uint8_t *const *filters_used, unsigned flags);
@@ -123,7 +125,8 @@ int oxi_filter_image_sharded(const oxi_ihdr *, const uint8_t *data, size_t data_
                              uint8_t *const *outs, uint8_t *const *filters_used, unsigned flags);
 
 /* ---- reduction scans, src/reduction/{alpha,bit_depth,color,palette}.rs ----------------------- */
-/* Every function: host buffers in, host buffers out; `out` must hold the stated worst case.
+/* Every function: host buffers in, host buffers out; `out` must hold the stated worst case (the handle -> handle
+ * variants further down allocate their result themselves).
  * out_ihdr / out_aux receive the IhdrData / ColorType payload of the returned image. */
 
 /* cleaned_alpha_channel, alpha.rs:11-32; out: data_len */

@@ -146,3 +146,64 @@ def test_batch_rejects_ragged_data_len():
     two = np.concatenate([d, d, np.zeros(5, np.uint8)])  # 2 images "of 64*4+2.5 bytes": not whole scanlines
     with pytest.raises(ox.OxiError):
         ox.filter_batch(img.ihdr, two[: 2 * (d.size + 2)], 2, [ox.FilterStrategy.NONE], False)
+
+
+def test_pageable_and_pinned_host_buffers_give_the_same_bytes():
+    """oxi_filter_batch stages pageable caller memory through its own pinned buffers with copy threads (several 32 MB
+    chunks, slots reused) and uses pinned caller memory in place: same bytes either way, equal to the oracle."""
+    import torch
+    import oxipng_b200 as ox
+    w, h, n = 1024, 256, 44  # 46 MB of input: more than one staging chunk, more chunks than slots with the outputs
+    imgs = [helpers.synth_image(w, h, 6, 8, 8000 + i, "photo" if i % 5 else "random")[1] for i in range(n)]
+    data = np.concatenate(imgs)
+    hdr = helpers.product_image((w, h, 6, 8, 0), imgs[0]).ihdr
+    S = ox.FilterStrategy
+    strat = [S.NONE, S.Bigrams, S.MinSum]
+    outs_p, used_p = ox.filter_batch(hdr, data, n, strat, False)  # numpy arrays: pageable
+    pin_in = torch.empty(data.size, dtype=torch.uint8, pin_memory=True)
+    pin_in.numpy()[:] = data
+    per = imgs[0].size + h
+    pin_out = [torch.empty(n * per, dtype=torch.uint8, pin_memory=True) for _ in strat]
+    pin_used = [torch.empty(n * h, dtype=torch.uint8, pin_memory=True) for _ in strat]
+    ox.filter_batch(hdr, pin_in.numpy(), n, strat, False, 0, [t.numpy() for t in pin_out], [t.numpy() for t in pin_used])
+    for j in range(len(strat)):
+        assert np.array_equal(outs_p[j], pin_out[j].numpy()), j
+        assert np.array_equal(used_p[j], pin_used[j].numpy()), j
+    kinds = [(oracle.BASIC, 0), (oracle.BIGRAMS, 0), (oracle.MINSUM, 0)]
+    for i in (0, 5, n - 1):
+        for j, (k, b) in enumerate(kinds):
+            want, wu, _ = oracle.filter_image((w, h, 6, 8, 0), imgs[i], k, b)
+            assert np.array_equal(outs_p[j][i * per:(i + 1) * per], want), (i, j)
+            assert np.array_equal(used_p[j][i * h:(i + 1) * h], wu), (i, j)
+
+
+def test_sharded_refuses_alpha_and_handles_reject_bad_arguments():
+    import ctypes as C
+    import oxipng_b200 as ox
+    from oxipng_b200 import shard
+    from oxipng_b200._lib import CIhdr, CStrategy, lib
+    from oxipng_b200.resident import DeviceImage, _setup
+    ih, d = helpers.synth_image(64, 32, 6, 8, 1, "transparent")
+    img = helpers.product_image(ih, d)
+    L = _setup(lib())
+    h = img.ihdr._c()
+    cs = (CStrategy * 1)()
+    cs[0], _k = ox.FilterStrategy.MinSum._c()
+    out = np.empty(d.size + 32, np.uint8)
+    used = np.empty(32, np.uint8)
+    po, pu = (C.c_void_p * 1)(out.ctypes.data), (C.c_void_p * 1)(used.ctypes.data)
+    devs = (C.c_int * 1)(0)
+    L.oxi_filter_image_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(CStrategy), C.c_size_t, C.c_int,
+                                           C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_void_p), C.c_uint]
+    # optimize_alpha with an alpha channel: rows are serial, no row bands
+    rc = L.oxi_filter_image_sharded(C.byref(h), C.c_void_p(d.ctypes.data), d.size, cs, 1, 1, devs, 1, 1, po, pu, 0)
+    assert rc == -4 and b"serial" in L.oxi_last_error()
+    # handles: a null image and a too small download buffer are errors, not crashes
+    assert L.oxi_image_info(None, None, None, None) < 0
+    dev = DeviceImage.upload(img)
+    small = np.empty(8, np.uint8)
+    got = C.c_size_t()
+    assert L.oxi_image_download(dev._h, C.c_void_p(small.ctypes.data), 8, C.byref(got)) < 0
+    out_h = C.c_void_p()
+    assert L.oxi_reduced_alpha_channel_device(None, 0, C.byref(out_h)) < 0
