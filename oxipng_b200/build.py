@@ -40,7 +40,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
         path = os.path.join(CSRC, src)
         if force or _stale(obj, [path] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            extra = os.environ.get("OXI_NVCC_EXTRA", "").split()  # e.g. -DUF_TRACE for a one-off instrumented build
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or r.returncode:
                 print(r.stdout + r.stderr)

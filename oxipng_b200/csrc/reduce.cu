@@ -7,6 +7,8 @@
 // global memory, per-CTA shared-memory partials (flags, 256-bin histograms, distinct-colour hash sets) merged with a
 // handful of global atomics per CTA.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -573,145 +575,304 @@ __global__ void __launch_bounds__(RT) k_deinterlace(const uint8_t *__restrict__ 
 
 // ---- unfilter_image (png/mod.rs:335-351, filters/mod.rs:188-239), SURVEY 8f row 1 ----------------------------------
 // Reconstruction is a recurrence along the row (Sub/Average/Paeth use the rebuilt left pixel) and across rows
-// (Up/Average/Paeth use the rebuilt previous row).  A warp takes a tile of 32 rows and walks it in skewed lockstep: at step s lane l rebuilds pixel s-l of row k0+l, so the pixel above it (lane l-1) was
-// finished in the step before and arrives by shuffle, "upleft" is the value shuffled in one step earlier and "left"
-// never leaves the lane's registers.
-__device__ __forceinline__ uint32_t paeth4_u(uint32_t a, uint32_t b, uint32_t c) { // byte-wise paeth_predictor
-    uint32_t r = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) r |= paeth((a >> (8 * j)) & 255u, (b >> (8 * j)) & 255u, (c >> (8 * j)) & 255u) << (8 * j);
-    return r;
+// (Up/Average/Paeth use the rebuilt previous row): the longest dependency chain of an image is width + height pixels.
+// A warp takes a *tile* of 32 consecutive rows, lane = row, and walks it in skewed lockstep: at step s lane l rebuilds
+// pixel s - delta(l) of its row.  delta is 0 for a row that does not look at the row above it (None, Sub, the first row
+// of a tile) and delta(l-1) + 1 otherwise, so the pixel above was finished by lane l-1 in the step before and arrives
+// by one shuffle, "upleft" is the value shuffled in one step earlier and "left" never leaves the lane's registers.
+// The rows of a tile use different filters: predictors are selected by per-lane masks instead of a divergent switch,
+// and the step body is instantiated three times (MODE) so that a tile without Paeth (or Average) rows does not pay
+// for that predictor.
+//
+// Tiles form a pipeline across warps, CTAs and SMs: the first row of tile t needs the last row of tile t-1 -- unless it
+// is a None/Sub row, then the tile is independent.  The producer publishes every pixel of its last row as one 64-bit
+// word (tile tag << 32 | pixel) in a per-tile boundary array; the consumer reads eight of them per sub-chunk, one
+// sub-chunk ahead of its use, and re-polls only the words whose tag is still missing.  Data and flag travel in the same
+// naturally-atomic word: no fence, no acquire/release pair, one L2 round trip off the dependency chain.  The consumer
+// trails its producer by delta(last row) + ~16 steps.  All CTAs of a launch are co-resident (cooperative launch,
+// grid <= #SMs) and a warp takes its tiles in increasing order, so waiting on tile t-1 cannot deadlock.
+//
+// Memory traffic stays off the step-to-step chain and off the LSU: a lane's row is a different cache line from its
+// neighbour's, so a per-lane load or store costs 32 tag cycles and four warps per SM would spend their time there
+// (measured: 320 cycles per step).  Instead the warp moves one row's piece at a time, lanes = consecutive words: the
+// filtered bytes of every row's next 32 pixels (16 for 6/8-byte pixels) arrive as aligned words by cp.async in a per-row
+// window of shared memory (33-word stride: conflict-free for the per-lane reads), the step extracts its pixel with two
+// LDS and one funnel shift and parks the result in a [row][pixel] array, and every row's 32 pixels leave with one
+// coalesced store.  Both transfers are software-pipelined INTO the steps: step j of chunk c also fetches row j of chunk
+// c+1 and stores row j of chunk c-1 (double-buffered windows and result arrays, branch-free: rows and pixels that do
+// not exist are clipped by one unsigned compare on tile-relative 32-bit offsets), so a lone warp per scheduler has
+// independent work to issue while the dependency chain of the step waits.
+constexpr int UF_WARPS = 4, UF_RAW = 33, UF_SUB = 8, UF_AHEAD = 1;
+// per-warp shared memory, in words: two windows x 32 rows, two result buffers of one or two [32][CH+1] arrays
+constexpr int uf_warp_words(int bpp) { return 2 * 32 * UF_RAW + 2 * (bpp > 4 ? 2 * 32 * 17 : 32 * 33); }
+constexpr uint32_t UF_MAX_ROW = 1u << 24; // tile-relative offsets are 32-bit: rows of 16 MB and more are refused
+
+struct UfPlan {
+    uint64_t ent_base[7]; // first boundary word of each pass (tile t of pass p: ent_base[p] + t * pixels)
+    uint64_t ent_words;   // words per boundary array (6/8-byte pixels use two arrays)
+    uint32_t ctas_per_item;
+};
+
+__device__ __forceinline__ uint32_t vadd4_keep(uint32_t d, uint32_t p, uint32_t keep) { // (d + p) per byte, & keep
+    const uint32_t s = (d & 0x7f7f7f7fu) + (p & 0x7f7f7f7fu);
+    return (s ^ ((d ^ p) & 0x80808080u)) & keep;
 }
-// n <= 4 bytes at any alignment, little endian: two aligned 32-bit loads + funnel shift (the second word is only read
-// when the bytes straddle it; buffers carry >= 4 bytes of slack).  CG = bypass L1 (data written by another warp).
-template <bool CG>
-__device__ __forceinline__ uint32_t ld_bytes(const uint8_t *p, int n) {
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
-    const uint32_t *q = reinterpret_cast<const uint32_t *>(p - mis);
-    const uint32_t w0 = CG ? __ldcg(q) : *q;
-    uint32_t w1 = 0;
-    if (mis + n > 4) w1 = CG ? __ldcg(q + 1) : q[1];
-    const uint32_t v = __funnelshift_r(w0, w1, 8 * mis);
-    return n >= 4 ? v : (v & ((1u << (8 * n)) - 1u));
+__device__ __forceinline__ unsigned long long ld_entry(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
-__device__ __forceinline__ void st_bytes(uint8_t *p, uint32_t v, int n) {
-    if (n == 4 && (reinterpret_cast<uintptr_t>(p) & 3u) == 0) {
-        *reinterpret_cast<uint32_t *>(p) = v;
+// Stores of the step loop are written as global-space asm WITHOUT a memory clobber: nothing in this thread reads them
+// back, and a generic store (or a clobber) would pin every shared-memory load of the unrolled steps behind it.
+__device__ __forceinline__ void st_entry(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v));
+}
+__device__ __forceinline__ void stg8(uint8_t *p, uint32_t v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v)); }
+__device__ __forceinline__ void stg16(uint8_t *p, uint32_t v) { asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v)); }
+__device__ __forceinline__ void stg32(uint8_t *p, uint32_t v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v)); }
+// one rebuilt pixel to global memory; p is aligned to the pixel's natural granule (2 for 2/6-byte pixels, 4 for 4, 8 for 8)
+template <int BPP>
+__device__ __forceinline__ void st_pixel(uint8_t *p, uint32_t r0, uint32_t r1) {
+    if constexpr (BPP == 1) {
+        stg8(p, r0);
+    } else if constexpr (BPP == 2) {
+        stg16(p, r0);
+    } else if constexpr (BPP == 3) {
+        stg8(p, r0); stg8(p + 1, r0 >> 8); stg8(p + 2, r0 >> 16);
+    } else if constexpr (BPP == 4) {
+        stg32(p, r0);
+    } else if constexpr (BPP == 6) {
+        stg16(p, r0); stg16(p + 2, r0 >> 16); stg16(p + 4, r1);
     } else {
-        for (int j = 0; j < n; j++) p[j] = (uint8_t)(v >> (8 * j));
+        asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(r0), "r"(r1));
     }
 }
-// UF_CTAS CTAs per (image, pass); their UF_CTAS x UF_WARPS warps take the 32-row tiles round-robin and run them as a
-// pipeline: the warp of tile t trails the warp of tile t-1 by 32 steps, because row 32t-1 (the row above its first row)
-// is produced by lane 31 of that warp.  Progress is published per warp in global memory every UF_CHUNK steps (the
-// pipeline spans SMs: one SM alone is bound by instruction issue, ~140 instructions per warp and step); the boundary row
-// goes through global memory as well (release store of the progress word by the lane that wrote it, the reader
-// bypasses L1 with ld.global.cg).  All CTAs of a launch are resident at once (grid <= 7 x 32 CTAs of 128 threads), so
-// waiting on an earlier tile cannot deadlock.
-// Memory latency stays off the step-to-step dependency chain: at the start of a chunk every lane fetches the filtered
-// bytes of its next UF_CHUNK pixels (and lane 0 the boundary pixels above them) with independent loads into a
-// per-warp shared-memory stage laid out [step][lane] (conflict-free), and the steps then read shared memory only.
-constexpr int UF_WARPS = 4, UF_CTAS = 32, UF_CHUNK = 32;
-constexpr uint32_t UF_STAGE_WORDS = 2 * UF_CHUNK * 32 + 2 * UF_CHUNK; // per warp: W0,W1[step][lane], B0,B1[step]
-// BPP = 4: specialisation for 4-byte pixels (RGBA8, gray+alpha 16): one word per pixel, no byte-count arithmetic in the
-// step (the generic body is ~290 instructions per step, all executed by a lone warp per scheduler); BPP = 0: any bpp.
+
+struct UfTile {
+    const uint8_t *src0;        // filtered row of the tile's first row (filter byte first); row l: + l * (len + 1)
+    uint8_t *dst0;              // rebuilt row of the tile's first row; row l: + l * len
+    const uint8_t *in_lo, *in_hi; // bounds of the filtered buffer (aligned word loads are clipped to them)
+    const unsigned long long *ent_in; // boundary words of tile t-1 (read when dep)
+    unsigned long long *ent_out;      // boundary words of this tile (written when pub)
+    uint64_t ent_words;
+    uint32_t len, npix, delta, maxd, lastlane, tag;
+    uint32_t m1, m2, m3, m4;
+    bool valid, dep, pub;
+};
+
+// MODE 0: None/Sub/Up rows only; 1: + Average; 2: + Paeth
+template <int BPP, int MODE>
+__device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t lane) {
+    constexpr int N1 = BPP > 4 ? BPP - 4 : 0;
+    constexpr int CH = BPP > 4 ? 16 : 32;          // pixels (= steps) per chunk
+    constexpr int RAWW = CH * BPP / 4 + 1;         // aligned words that hold a chunk at any misalignment (<= 33)
+    constexpr int RAWL = RAWW < 32 ? RAWW : 32;    // of them, moved by the row-wise copy (word 32 by the row's own lane)
+    constexpr int OS = CH + 1;                     // stride of the result arrays
+    constexpr int OBUF = (N1 ? 2 : 1) * 32 * OS;   // words per result buffer
+    constexpr int NOROW = -(1 << 30);              // offset of a row that does not exist: fails every range check
+    uint32_t *raw = sm, *O = sm + 2 * 32 * UF_RAW;
+    const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(raw);
+    const uint32_t nchunks = (T.npix + T.maxd + CH - 1) / CH;
+    // this lane's row, relative to the tile: first byte of chunk 0's window (pixel -delta), aligned down to a word
+    const int p0 = (int)(lane * (T.len + 1) + 1) - (int)(T.delta * BPP);
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(T.src0 + p0) & 3u);
+    const int srcoff = T.valid ? p0 - (int)mis : NOROW;
+    const int dstoff = T.valid ? (int)(lane * T.len) - (int)(T.delta * BPP) : NOROW;
+    const ptrdiff_t lo_d = T.in_lo - T.src0, hi_d = T.in_hi - T.src0;
+    const int lo_rel = lo_d < -(ptrdiff_t)(1 << 29) ? -(1 << 29) : (int)lo_d;
+    const int hi_rel = hi_d > (ptrdiff_t)0x7fffffff ? 0x7fffffff : (int)hi_d;
+    const unsigned long long want = T.tag; // tag of tile t-1's words = t (its index + 1)
+    const bool publane = T.pub && lane == T.lastlane;
+
+    // row r's words of a chunk -> its window; lanes = consecutive words of that row.  win_s: shared address of this
+    // lane's word of row 0 in the destination window, add: the chunk's byte offset + 4 * lane
+    auto fetch_row = [&](uint32_t win_s, int add, int r) {
+        const int pos = __shfl_sync(0xffffffffu, srcoff, r) + add;
+        if (lane < RAWL && pos >= lo_rel && pos < hi_rel)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(win_s + r * (UF_RAW * 4)), "l"(T.src0 + pos));
+    };
+    auto fetch_own_tail = [&](uint32_t cc) { // word 32 of this lane's own window
+        if (RAWW > 32) {
+            const int pos = srcoff + (int)(cc * (CH * BPP)) + 128;
+            if (pos >= lo_rel && pos < hi_rel)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(raw_s + (((cc & 1u) * 32u + lane) * UF_RAW + 32u) * 4u), "l"(T.src0 + pos));
+        }
+    };
+    const int st_row = CH == 16 ? (int)(lane & 16u) : 0, st_px = CH == 16 ? (int)(lane & 15u) : (int)lane;
+
+    uint32_t l0 = 0, l1 = 0, ul0 = 0, ul1 = 0; // rebuilt left pixel, upleft pixel
+    // boundary words of the current sub-chunk (c0/c1, lanes 0..UF_SUB-1) and of the next UF_AHEAD ones: a word is
+    // requested UF_AHEAD sub-chunks before its use (an L2 round trip is several steps long) and re-polled at its use
+    // only if its tag was still missing then
+    unsigned long long c0 = 0, c1 = 0, e0[UF_AHEAD] = {}, e1[UF_AHEAD] = {};
+    if (T.dep && lane < UF_SUB) {
+        if (lane < T.npix) {
+            c0 = ld_entry(T.ent_in + lane);
+            if (N1) c1 = ld_entry(T.ent_in + T.ent_words + lane);
+        }
+#pragma unroll
+        for (int a = 0; a + 1 < UF_AHEAD; a++)
+            if (lane + (a + 1) * UF_SUB < T.npix) {
+                e0[a] = ld_entry(T.ent_in + lane + (a + 1) * UF_SUB);
+                if (N1) e1[a] = ld_entry(T.ent_in + T.ent_words + lane + (a + 1) * UF_SUB);
+            }
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int r = 0; r < 32; r++) fetch_row(raw_s + 4u * lane, 4 * (int)lane, r);
+    fetch_own_tail(0);
+    // one extra iteration: its steps are idle (every pixel is past the row's end), its stores drain the last chunk
+    for (uint32_t c = 0; c <= nchunks; c++) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp(); // windows of chunk c complete, results of chunk c-1 visible, stores of chunk c-2 have read their buffer
+        fetch_own_tail(c + 1);
+        const uint32_t *lb = raw + ((c & 1u) * 32u + lane) * UF_RAW;
+        uint32_t *ob0 = O + (c & 1u) * OBUF + lane * OS, *ob1 = ob0 + 32 * OS;
+        const uint32_t *sb = O + ((c + 1u) & 1u) * OBUF + st_row * OS + st_px; // results of chunk c-1, this lane's share
+        const uint32_t next_s = raw_s + (((c + 1u) & 1u) * 32u * UF_RAW + lane) * 4u;
+        const int next_add = (int)((c + 1u) * (CH * BPP)) + 4 * (int)lane;
+        const int st_add = ((int)(c * CH) - CH + st_px) * BPP; // chunk c-1 ("-1": nothing passes the range check)
+        const int x0 = (int)(c * CH) - (int)T.delta; // this lane's pixel at the chunk's first step
+#pragma unroll
+        for (int q = 0; q < CH / UF_SUB; q++) {
+            if (T.dep) {
+                const uint32_t xs = c * CH + q * UF_SUB + lane; // lane 0's row is at delta 0: step == pixel
+                for (;;) {
+                    const bool ok = lane >= UF_SUB || xs >= T.npix ||
+                                    ((c0 >> 32) == want && (!N1 || (c1 >> 32) == want));
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (!ok) {
+                        c0 = ld_entry(T.ent_in + xs);
+                        if (N1) c1 = ld_entry(T.ent_in + T.ent_words + xs);
+                    }
+                }
+                // requested only now, AFTER the check: the check waits on the scoreboard these loads share, so a
+                // request issued in front of it would be waited for as well (measured: one exposed L2 round trip per
+                // sub-chunk, 224 instead of 121 cycles per step)
+                if (lane < UF_SUB && xs + UF_AHEAD * UF_SUB < T.npix) {
+                    e0[UF_AHEAD - 1] = ld_entry(T.ent_in + xs + UF_AHEAD * UF_SUB);
+                    if (N1) e1[UF_AHEAD - 1] = ld_entry(T.ent_in + T.ent_words + xs + UF_AHEAD * UF_SUB);
+                }
+            }
+            // every shared-memory read of the sub-chunk up front (ptxas keeps LDS behind an earlier LDGSTS, so a load
+            // inside the steps would sit right in front of its use): the filtered pixels of the sub-chunk and the result
+            // words this lane stores for chunk c-1
+            uint32_t d0[UF_SUB], d1[UF_SUB], s0[UF_SUB], s1[UF_SUB];
+#pragma unroll
+            for (int jj = 0; jj < UF_SUB; jj++) {
+                const int j = q * UF_SUB + jj;
+                const uint32_t o = mis + j * BPP; // bytes [o, o + BPP) of the window
+                const uint32_t *wp = lb + (o >> 2);
+                const uint32_t w0 = wp[0], w1 = wp[1];
+                d0[jj] = __funnelshift_r(w0, w1, 8u * o);
+                d1[jj] = N1 ? __funnelshift_r(w1, wp[2], 8u * o) : 0u;
+                s0[jj] = sb[j * OS];
+                s1[jj] = N1 ? sb[j * OS + 32 * OS] : 0u;
+            }
+#pragma unroll
+            for (int jj = 0; jj < UF_SUB; jj++) {
+                const int j = q * UF_SUB + jj;
+                // pixel above: lane l-1's result of the previous step; lane 0: the boundary word
+                uint32_t a0 = __shfl_up_sync(0xffffffffu, l0, 1);
+                uint32_t a1 = N1 ? __shfl_up_sync(0xffffffffu, l1, 1) : 0u;
+                const uint32_t b0 = __shfl_sync(0xffffffffu, (uint32_t)c0, jj);
+                const uint32_t b1 = N1 ? __shfl_sync(0xffffffffu, (uint32_t)c1, jj) : 0u;
+                if (lane == 0) { a0 = b0; a1 = b1; }
+                const int x = x0 + j;
+                const bool act = T.valid && (uint32_t)x < T.npix;
+                const uint32_t keep = act ? ~0u : 0u;
+                uint32_t p0 = (l0 & T.m1) | (a0 & T.m2), p1 = 0;
+                if (N1) p1 = (l1 & T.m1) | (a1 & T.m2);
+                if (MODE >= 1) {
+                    p0 |= __vhaddu4(l0, a0) & T.m3;
+                    if (N1) p1 |= __vhaddu4(l1, a1) & T.m3;
+                }
+                if (MODE >= 2) {
+                    p0 |= paeth4(l0, a0, ul0) & T.m4;
+                    if (N1) p1 |= paeth4(l1, a1, ul1) & T.m4;
+                }
+                l0 = vadd4_keep(d0[jj], p0, keep);
+                if (N1) l1 = vadd4_keep(d1[jj], p1, keep);
+                ul0 = a0; ul1 = a1;
+                ob0[j] = l0;
+                if (N1) ob1[j] = l1;
+                if (publane && act) {
+                    st_entry(T.ent_out + x, ((unsigned long long)(T.tag + 1) << 32) | l0);
+                    if (N1) st_entry(T.ent_out + T.ent_words + x, ((unsigned long long)(T.tag + 1) << 32) | l1);
+                }
+                // off the chain: next chunk's row(s) in, previous chunk's row(s) out
+                fetch_row(next_s, next_add, j);
+                if (CH == 16) fetch_row(next_s, next_add, j + 16);
+                const int rr = j + st_row;
+                const int pos = __shfl_sync(0xffffffffu, dstoff, rr) + st_add;
+                if ((uint32_t)(pos - rr * (int)T.len) < T.len) st_pixel<BPP>(T.dst0 + pos, s0[jj], s1[jj]);
+            }
+            if (T.dep) {
+                c0 = e0[0]; c1 = e1[0];
+#pragma unroll
+                for (int a = 0; a + 1 < UF_AHEAD; a++) { e0[a] = e0[a + 1]; e1[a] = e1[a + 1]; }
+            }
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+}
+
 template <int BPP>
 __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_t *__restrict__ in, uint8_t *out,
                                                             uint64_t n_images, uint64_t in_stride, ScanState *st,
-                                                            unsigned long long *progress) {
-    __shared__ __align__(16) uint32_t uf_stage[UF_WARPS * UF_STAGE_WORDS];
+                                                            unsigned long long *ent, UfPlan plan) {
+    extern __shared__ __align__(16) uint32_t uf_smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *W0 = uf_stage + warp * UF_STAGE_WORDS, *W1 = W0 + UF_CHUNK * 32, *B0 = W1 + UF_CHUNK * 32, *B1 = B0 + UF_CHUNK;
-    const uint64_t item = blockIdx.x / UF_CTAS; // (image, pass)
+    const uint64_t item = blockIdx.x / plan.ctas_per_item; // (image, pass)
     if (item >= n_images * g.n_pass) return;
-    const uint32_t gw = (blockIdx.x % UF_CTAS) * UF_WARPS + warp, NW = UF_CTAS * UF_WARPS; // warp of the item's pipeline
+    const uint32_t gw = (blockIdx.x % plan.ctas_per_item) * UF_WARPS + warp, NW = plan.ctas_per_item * UF_WARPS;
     const uint64_t img = item / g.n_pass;
-    const PassDesc pd = g.pass[item % g.n_pass];
-    const int bpp = BPP ? BPP : (int)g.bpp, n0 = bpp < 4 ? bpp : 4, n1 = bpp - n0; // pixel = word0 (n0 bytes) + word1 (n1 bytes)
-    const uint32_t len = pd.len, npix = len / bpp;
+    const uint32_t pass = (uint32_t)(item % g.n_pass);
+    const PassDesc pd = g.pass[pass];
+    const uint32_t len = pd.len, npix = len / BPP;
     // filtered stream: row r of the image starts at in_base + r (one filter byte per earlier row), then 1 + len bytes
     const uint8_t *src = in + img * in_stride + pd.in_base + pd.row0;
     uint8_t *dst = out + img * g.data_len + pd.in_base;
-    const uint32_t ntiles = (pd.nrows + 31) / 32, steps = npix + 31;
-    // progress[item * NW + w] = (tile << 32) | steps finished, per pipeline warp
+    const uint32_t ntiles = (pd.nrows + 31) / 32;
+    unsigned long long *ebase = ent + img * plan.ent_words * 2 + plan.ent_base[pass];
+    UfTile T;
+    T.in_lo = in;
+    T.in_hi = in + n_images * in_stride;
+    T.ent_words = plan.ent_words;
+    T.npix = npix;
+    T.len = len;
     for (uint32_t t = gw; t < ntiles; t += NW) {
         const uint32_t k = t * 32 + lane;
-        const bool valid = k < pd.nrows;
-        const uint8_t *frow = src + (uint64_t)k * (len + 1);
-        uint8_t *orow = dst + (uint64_t)k * len;
-        uint32_t f = valid ? frow[0] : 0;
+        T.valid = k < pd.nrows;
+        T.src0 = src + (uint64_t)t * 32 * (len + 1);
+        T.dst0 = dst + (uint64_t)t * 32 * len;
+        uint32_t f = T.valid ? T.src0[(uint64_t)lane * (len + 1)] : 0;
         if (f > 4) { st->fail = 1; f = 0; } // RowFilter::try_from fails -> PngError::InvalidData
-        const uint32_t m1 = f == 1 ? ~0u : 0u, m2 = f == 2 ? ~0u : 0u, m3 = f == 3 ? ~0u : 0u, m4 = f == 4 ? ~0u : 0u;
-        const uint8_t *uprow = (lane == 0 && k > 0) ? orow - len : nullptr; // last row of tile t-1 (or zeros for row 0)
-        const uint32_t pw = (gw + NW - 1) % NW;                            // pipeline warp that runs tile t-1
-        uint32_t l0 = 0, l1 = 0, u0 = 0, u1 = 0; // left pixel (own last result), up pixel of the previous step
-        for (uint32_t s0 = 0; s0 < steps; s0 += UF_CHUNK) {
-            const uint32_t s1 = min(s0 + UF_CHUNK, steps);
-            // stage this lane's filtered pixels of the chunk: independent loads, one memory latency per chunk
-#pragma unroll 16
-            for (uint32_t j = 0; j < UF_CHUNK; j++) {
-                const int x = (int)(s0 + j) - (int)lane;
-                uint32_t d0 = 0, d1 = 0;
-                if (valid && x >= 0 && x < (int)npix) {
-                    d0 = ld_bytes<false>(frow + 1 + (size_t)x * bpp, n0);
-                    if (n1) d1 = ld_bytes<false>(frow + 1 + (size_t)x * bpp + 4, n1);
-                }
-                W0[j * 32 + lane] = d0;
-                if (n1) W1[j * 32 + lane] = d1;
-            }
-            if (t > 0) { // lane 0 reads pixels [s0, s1) of row 32t-1: finished by tile t-1 at its step x + 32
-                const unsigned long long need = ((unsigned long long)(t - 1) << 32) | min(s1 + 31, steps);
-                if (lane == 0) { // acquire: the boundary pixels read below were written before the progress word
-                    unsigned long long seen;
-                    do {
-                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(progress + item * NW + pw) : "memory");
-                    } while (seen < need);
-                }
-                __syncwarp();
-            }
-            if (lane == 0) {
-#pragma unroll 16
-                for (uint32_t j = 0; j < UF_CHUNK; j++) {
-                    const uint32_t x = s0 + j;
-                    uint32_t a0 = 0, a1 = 0;
-                    if (uprow && x < npix) {
-                        const uint8_t *u = uprow + (size_t)x * bpp;
-                        a0 = ld_bytes<true>(u, n0);
-                        if (n1) a1 = ld_bytes<true>(u + 4, n1);
-                    }
-                    B0[j] = a0;
-                    B1[j] = a1;
-                }
-            }
-            __syncwarp();
-#pragma unroll 4
-            for (uint32_t s = s0; s < s1; s++) {
-                const uint32_t j = s - s0;
-                // pixel above: the lane above finished it in the previous step
-                uint32_t a0 = __shfl_up_sync(0xffffffffu, l0, 1), a1 = n1 ? __shfl_up_sync(0xffffffffu, l1, 1) : 0u;
-                const int x = (int)s - (int)lane;
-                const bool act = valid && x >= 0 && x < (int)npix;
-                if (lane == 0) { a0 = B0[j]; a1 = B1[j]; }
-                if (act) {
-                    const uint32_t d0 = W0[j * 32 + lane];
-                    const uint32_t d1 = n1 ? W1[j * 32 + lane] : 0u;
-                    // the rows of a tile use different filters: select by per-row masks instead of a divergent switch
-                    const uint32_t p0 = (l0 & m1) | (a0 & m2) | (__vhaddu4(l0, a0) & m3) | (paeth4(l0, a0, u0) & m4);
-                    const uint32_t p1 = n1 ? (l1 & m1) | (a1 & m2) | (__vhaddu4(l1, a1) & m3) | (paeth4(l1, a1, u1) & m4) : 0u;
-                    const uint32_t r0 = __vadd4(d0, p0), r1 = __vadd4(d1, p1);
-                    st_bytes(orow + (size_t)x * bpp, r0, n0);
-                    if (n1) st_bytes(orow + (size_t)x * bpp + 4, r1, n1);
-                    l0 = r0; l1 = r1;
-                }
-                u0 = a0; u1 = a1; // becomes "upleft" of the next step
-            }
-            // only the tile's last row is read by another warp, and lane 31 wrote all of it: its release store orders
-            // those pixels before the progress word (no device-wide fence on the critical path)
-            if (lane == 31) {
-                const unsigned long long done = ((unsigned long long)t << 32) | s1;
-                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(progress + item * NW + gw), "l"(done) : "memory");
-            }
-        }
+        T.m1 = f == 1 ? ~0u : 0u; T.m2 = f == 2 ? ~0u : 0u; T.m3 = f == 3 ? ~0u : 0u; T.m4 = f == 4 ? ~0u : 0u;
+        // delta: rows since the last row that does not depend on the row above it
+        const uint32_t heads = __ballot_sync(0xffffffffu, !T.valid || f <= 1 || lane == 0);
+        T.delta = lane - (31u - (uint32_t)__clz((int)(heads & (0xffffffffu >> (31u - lane)))));
+        T.maxd = __reduce_max_sync(0xffffffffu, T.valid ? T.delta : 0u);
+        const uint32_t f_first = __shfl_sync(0xffffffffu, f, 0);
+        T.dep = t > 0 && f_first >= 2; // the tile's first row needs tile t-1's last row (row 0 of a pass: zeros)
+        T.pub = t + 1 < ntiles;
+        T.lastlane = min(31u, pd.nrows - 1u - t * 32u);
+        T.tag = t;
+        T.ent_out = ebase + (uint64_t)t * npix;
+        T.ent_in = ebase + (uint64_t)(t ? t - 1 : 0) * npix;
+        const bool any_avg = __any_sync(0xffffffffu, f == 3), any_paeth = __any_sync(0xffffffffu, f == 4);
+        uint32_t *sm = uf_smem + warp * uf_warp_words(BPP);
+#ifdef UF_TRACE
+        unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#endif
+        if (any_paeth) uf_run<BPP, 2>(T, sm, lane);
+        else if (any_avg) uf_run<BPP, 1>(T, sm, lane);
+        else uf_run<BPP, 0>(T, sm, lane);
+#ifdef UF_TRACE
+        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (lane == 0 && t < 128) { st->hist[t] = t0; st->hist[128 + t] = t1; }
+#endif
     }
 }
 
@@ -1307,27 +1468,60 @@ int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, u
     }
     build_geom(h, lo, 0, &g);
     if (g.total_rows == 0) { if (out_len) *out_len = 0; return OXI_OK; }
-    const size_t prog_bytes = (size_t)g.n_pass * UF_CTAS * UF_WARPS * sizeof(unsigned long long);
-    Call call(filtered, len, out, g.data_len, prog_bytes);
+    if (g.max_len >= UF_MAX_ROW) return fail(OXI_E_UNSUPPORTED, "scanlines of 16 MB and more are not supported");
+    if (t_devio && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(filtered)) & 15u))
+        return fail(OXI_E_ARG, "device buffers must be 16-byte aligned");
+    // boundary words: one per pixel and tile (6/8-byte pixels: two arrays), zeroed so that no tag matches yet
+    UfPlan plan{};
+    uint32_t max_tiles = 1;
+    for (uint32_t p = 0; p < g.n_pass; p++) {
+        const uint32_t ntiles = (g.pass[p].nrows + 31) / 32;
+        plan.ent_base[p] = plan.ent_words;
+        plan.ent_words += (uint64_t)ntiles * (g.pass[p].len / g.bpp);
+        max_tiles = std::max(max_tiles, ntiles);
+    }
+    const size_t ent_bytes = (size_t)plan.ent_words * 2 * sizeof(unsigned long long);
+    Call call(filtered, len, out, g.data_len, ent_bytes);
     if (!call.ok()) return call.err;
-    unsigned long long *prog = reinterpret_cast<unsigned long long *>(call.extra);
-    if (cudaMemsetAsync(prog, 0, prog_bytes, call.stream) != cudaSuccess) return fail(OXI_E_CUDA, "memset(progress)");
+    unsigned long long *ent = reinterpret_cast<unsigned long long *>(call.extra);
+    if (cudaMemsetAsync(ent, 0, g.bpp > 4 ? ent_bytes : ent_bytes / 2, call.stream) != cudaSuccess)
+        return fail(OXI_E_CUDA, "memset(boundary words)");
     {
         // the tiles of a pass wait on each other across CTAs: a cooperative launch guarantees that all of them are
-        // resident together (<= 7 x 32 CTAs of 128 threads) even when other streams keep the device busy
+        // resident together (grid <= #SMs: one CTA per SM, one pipeline warp per scheduler) even when other streams keep
+        // the device busy
+        plan.ctas_per_item = std::max(1u, std::min((max_tiles + UF_WARPS - 1) / UF_WARPS, (uint32_t)call.c->num_sms / g.n_pass));
         uint64_t one = 1, stride = len;
         const uint8_t *din = call.d_in;
         uint8_t *dout = call.d_out;
         ScanState *sst = call.st;
-        void *args[] = {&g, &din, &dout, &one, &stride, &sst, &prog};
-        const void *fn = g.bpp == 4 ? (const void *)k_unfilter<4> : (const void *)k_unfilter<0>;
-        cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(g.n_pass * UF_CTAS), dim3(UF_WARPS * 32),
-                                                    args, 0, call.stream);
+        void *args[] = {&g, &din, &dout, &one, &stride, &sst, &ent, &plan};
+        const void *fn = nullptr;
+        switch (g.bpp) {
+        case 1: fn = (const void *)k_unfilter<1>; break;
+        case 2: fn = (const void *)k_unfilter<2>; break;
+        case 3: fn = (const void *)k_unfilter<3>; break;
+        case 4: fn = (const void *)k_unfilter<4>; break;
+        case 6: fn = (const void *)k_unfilter<6>; break;
+        case 8: fn = (const void *)k_unfilter<8>; break;
+        default: return fail(OXI_E_ARG, "unsupported filter bpp");
+        }
+        // always the same value for a given instantiation: concurrent callers cannot shrink each other's limit
+        const size_t smem = (size_t)UF_WARPS * uf_warp_words((int)g.bpp) * sizeof(uint32_t);
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaLaunchCooperativeKernel(fn, dim3(g.n_pass * plan.ctas_per_item), dim3(UF_WARPS * 32), args, smem, call.stream);
         if (e != cudaSuccess) return fail_cuda(e, "cudaLaunchCooperativeKernel(k_unfilter)");
     }
     if (int rc = call.check("k_unfilter")) return rc;
     ScanState st;
     if (int rc = call.state(&st)) return rc;
+#ifdef UF_TRACE
+    if (getenv("OXI_UF_TRACE")) {
+        for (int t = 0; t < 128; t++)
+            fprintf(stderr, "tile %d start %.2f end %.2f us\n", t, (double)(st.hist[t] - st.hist[0]) / 1e3, (double)(st.hist[128 + t] - st.hist[0]) / 1e3);
+    }
+#endif
     if (st.fail) return fail(OXI_E_DATA, "invalid filter type byte (PngError::InvalidData)");
     if (int rc = call.download(out, g.data_len)) return rc;
     if (out_len) *out_len = g.data_len;

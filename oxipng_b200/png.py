@@ -284,6 +284,21 @@ def unfilter_image(ihdr: IhdrData, filtered) -> np.ndarray:
     return out[:n.value]
 
 
+def unfilter_image_device(ihdr: IhdrData, d_filtered: int, length: int, d_out: int, device: int = 0, stream: int = 0) -> int:
+    """oxi_unfilter_image_device: the inflated stream and the result are device pointers (e.g. torch tensors'
+    data_ptr()); returns the number of bytes written to d_out."""
+    h = ihdr._c()
+    n = C.c_size_t(0)
+    L = lib()
+    L.oxi_unfilter_image_device.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    rc = L.oxi_unfilter_image_device(device, C.c_void_p(stream), C.byref(h), C.c_void_p(d_filtered), C.c_size_t(length),
+                                     C.c_void_p(d_out), C.byref(n))
+    if rc == -5:
+        raise ValueError("invalid filter type byte")
+    check(rc, "oxi_unfilter_image_device")
+    return n.value
+
+
 def interlace_image(png: PngImage) -> PngImage:
     """interlace_image (interlace.rs:6-60): progressive -> Adam7 layout."""
     h = png.ihdr._c()

@@ -40,6 +40,29 @@ def test_unfilter_inverts_every_strategy_and_matches_oracle():
                     assert np.array_equal(got, oracle.unfilter_image(ih, filtered))
 
 
+def test_unfilter_tile_pipeline_tall_images():
+    """many 32-row tiles: long runs of rows that depend on the row above (tile-to-tile boundary words), runs broken by
+    None/Sub rows (independent tiles), more tiles than pipeline warps, every pixel size"""
+    import oxipng_b200 as ox
+    rng = np.random.default_rng(5)
+    cases = [(6, 8, 70, 700), (2, 8, 33, 1300), (0, 8, 300, 330), (4, 8, 64, 257), (6, 16, 45, 420), (2, 16, 31, 390),
+             (3, 4, 100, 513), (4, 16, 9, 2100), (6, 8, 3, 25000)]
+    for ct, bd, w, h in cases:
+        ih, d = helpers.synth_image(w, h, ct, bd, 3 + w, "photo")
+        hdr = helpers.product_image(ih, d).ihdr
+        lists = [np.full(h, 4, np.uint8), np.full(h, 3, np.uint8), rng.integers(2, 5, h).astype(np.uint8),
+                 rng.integers(0, 5, h).astype(np.uint8),
+                 np.where(rng.random(h) < 0.03, 1, rng.integers(2, 5, h)).astype(np.uint8)]
+        for i, pre in enumerate(lists):
+            filtered, used, _ = oracle.filter_image(ih, d, oracle.PREDEFINED, 0, pre)
+            assert np.array_equal(np.asarray(used), pre)
+            got = ox.unfilter_image(hdr, filtered)
+            assert np.array_equal(got, d), (ct, bd, w, h, i)
+        il_ih, il_d = helpers.synth_image(w, min(h, 600), ct, bd, 5, "photo", True)
+        filtered, _, _ = oracle.filter_image(il_ih, il_d, oracle.MINSUM, 0)
+        assert np.array_equal(ox.unfilter_image(helpers.product_image(il_ih, il_d).ihdr, filtered), il_d), (ct, bd, w, h)
+
+
 def test_unfilter_golden_fixtures(golden):
     """the reference's own files: stream as stored in the PNG (whatever filters its encoder chose) -> pixels"""
     import oxipng_b200 as ox
