@@ -172,9 +172,15 @@ int oxi_apply_palette_reorder(const oxi_ihdr *, const oxi_color_aux *, const uin
  * inflated IDAT stream (one filter-type byte in front of every scanline) -> PngImage.data. out: len bytes suffice.
  * Returns OXI_E_DATA for a filter type > 4 (the reference's PngError::InvalidData). */
 int oxi_unfilter_image(const oxi_ihdr *, const uint8_t *filtered, size_t len, uint8_t *out, size_t *out_len);
+/* n_images inflated streams of identical IHDR and length `len`, back to back (what a decoder front end hands over for a
+ * directory of equally sized images) -> n_images x *out_len bytes of pixels, back to back.  One launch: groups of CTAs
+ * walk the images, so the device is filled even though one image's rows form a dependency chain. */
+int oxi_unfilter_batch(const oxi_ihdr *, const uint8_t *filtered, size_t len, size_t n_images, uint8_t *out, size_t *out_len);
 /* the same with the inflated stream already in HBM: d_filtered (len bytes) and d_out are device pointers on `device`,
  * the work is enqueued on `stream`; only the few-byte "invalid filter type" flag is read back (synchronises) */
 int oxi_unfilter_image_device(int device, void *stream, const oxi_ihdr *, const uint8_t *d_filtered, size_t len,
+                              uint8_t *d_out, size_t *out_len);
+int oxi_unfilter_batch_device(int device, void *stream, const oxi_ihdr *, const uint8_t *d_filtered, size_t len, size_t n_images,
                               uint8_t *d_out, size_t *out_len);
 /* interlace_image, src/interlace.rs:6-60: progressive layout -> Adam7 layout (ihdr describes the image; its
  * `interlaced` flag is ignored). out: oxi_raw_data_size(interlaced ihdr) - rows bytes at most (<= data_len + 7*height). */

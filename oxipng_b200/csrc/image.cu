@@ -250,6 +250,16 @@ int oxi_unfilter_image_device(int device, void *stream, const oxi_ihdr *h, const
     return oxi_unfilter_image(h, d_filtered, len, d_out, out_len);
 }
 
+int oxi_unfilter_batch_device(int device, void *stream, const oxi_ihdr *h, const uint8_t *d_filtered, size_t len, size_t n_images,
+                              uint8_t *d_out, size_t *out_len) {
+    if (!d_filtered || !d_out) return fail(OXI_E_ARG, "bad arguments");
+    DeviceCtx *c;
+    if (int rc = bind(device, &c)) return rc;
+    const DevIO io{device, (cudaStream_t)stream};
+    DevIOScope scope(&io);
+    return oxi_unfilter_batch(h, d_filtered, len, n_images, d_out, out_len);
+}
+
 // ---- the filter search on a resident image ---------------------------------------------------------------------------
 
 int oxi_image_filter_device(const oxi_image *im, const oxi_strategy *strategies, size_t k, int optimize_alpha,

@@ -609,7 +609,8 @@ constexpr uint32_t UF_MAX_ROW = 1u << 24; // tile-relative offsets are 32-bit: r
 
 struct UfPlan {
     uint64_t ent_base[7]; // first boundary word of each pass (tile t of pass p: ent_base[p] + t * pixels)
-    uint64_t ent_words;   // words per boundary array (6/8-byte pixels use two arrays)
+    uint64_t ent_words;   // words per boundary array of one image
+    uint32_t ent_arrays;  // 1, or 2 for 6/8-byte pixels (second pixel word)
     uint32_t ctas_per_item;
 };
 
@@ -824,9 +825,13 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
                                                             unsigned long long *ent, UfPlan plan) {
     extern __shared__ __align__(16) uint32_t uf_smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t item = blockIdx.x / plan.ctas_per_item; // (image, pass)
-    if (item >= n_images * g.n_pass) return;
+    // a group of ctas_per_item CTAs walks the (image, pass) items group, group + #groups, ...: every warp of the group takes
+    // the items in the same order and an item's tiles wait only on tiles of the same item, so a batch needs no more
+    // co-resident CTAs than fit on the device
+    const uint32_t group = blockIdx.x / plan.ctas_per_item, ngroups = gridDim.x / plan.ctas_per_item;
     const uint32_t gw = (blockIdx.x % plan.ctas_per_item) * UF_WARPS + warp, NW = plan.ctas_per_item * UF_WARPS;
+    if (group >= ngroups) return;
+    for (uint64_t item = group; item < n_images * g.n_pass; item += ngroups) {
     const uint64_t img = item / g.n_pass;
     const uint32_t pass = (uint32_t)(item % g.n_pass);
     const PassDesc pd = g.pass[pass];
@@ -835,7 +840,7 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
     const uint8_t *src = in + img * in_stride + pd.in_base + pd.row0;
     uint8_t *dst = out + img * g.data_len + pd.in_base;
     const uint32_t ntiles = (pd.nrows + 31) / 32;
-    unsigned long long *ebase = ent + img * plan.ent_words * 2 + plan.ent_base[pass];
+    unsigned long long *ebase = ent + img * plan.ent_words * plan.ent_arrays + plan.ent_base[pass];
     UfTile T;
     T.in_lo = in;
     T.in_hi = in + n_images * in_stride;
@@ -873,6 +878,7 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
         unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (lane == 0 && t < 128) { st->hist[t] = t0; st->hist[128 + t] = t1; }
 #endif
+    }
     }
 }
 
@@ -1454,9 +1460,10 @@ int oxi_deinterlace_image(const oxi_ihdr *h, const uint8_t *data, size_t len, ui
 }
 
 
-int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, uint8_t *out, size_t *out_len) {
-    if (!valid_ihdr(h) || !filtered || !out) return fail(OXI_E_ARG, "bad arguments");
-    // geometry of the unfiltered data this stream holds: every scanline carries one extra byte
+// n_images filtered streams of `len` bytes each, back to back -> n_images x data_len bytes of pixels, back to back
+static int unfilter_streams(const oxi_ihdr *h, const uint8_t *filtered, size_t len, size_t n_images, uint8_t *out, size_t *out_len) {
+    if (!valid_ihdr(h) || !filtered || !out || n_images == 0) return fail(OXI_E_ARG, "bad arguments");
+    // geometry of the unfiltered data a stream holds: every scanline carries one extra byte
     // (ScanLines with has_filter = true, png/scan_lines.rs:159-163)
     Geom g;
     size_t lo = 0, hi = len; // find data_len such that data_len + rows(data_len) is the largest value <= len
@@ -1480,22 +1487,13 @@ int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, u
         plan.ent_words += (uint64_t)ntiles * (g.pass[p].len / g.bpp);
         max_tiles = std::max(max_tiles, ntiles);
     }
-    const size_t ent_bytes = (size_t)plan.ent_words * 2 * sizeof(unsigned long long);
-    Call call(filtered, len, out, g.data_len, ent_bytes);
+    plan.ent_arrays = g.bpp > 4 ? 2 : 1;
+    const size_t ent_bytes = (size_t)plan.ent_words * plan.ent_arrays * n_images * sizeof(unsigned long long);
+    Call call(filtered, len * n_images, out, (size_t)g.data_len * n_images, ent_bytes);
     if (!call.ok()) return call.err;
     unsigned long long *ent = reinterpret_cast<unsigned long long *>(call.extra);
-    if (cudaMemsetAsync(ent, 0, g.bpp > 4 ? ent_bytes : ent_bytes / 2, call.stream) != cudaSuccess)
-        return fail(OXI_E_CUDA, "memset(boundary words)");
+    if (cudaMemsetAsync(ent, 0, ent_bytes, call.stream) != cudaSuccess) return fail(OXI_E_CUDA, "memset(boundary words)");
     {
-        // the tiles of a pass wait on each other across CTAs: a cooperative launch guarantees that all of them are
-        // resident together (grid <= #SMs: one CTA per SM, one pipeline warp per scheduler) even when other streams keep
-        // the device busy
-        plan.ctas_per_item = std::max(1u, std::min((max_tiles + UF_WARPS - 1) / UF_WARPS, (uint32_t)call.c->num_sms / g.n_pass));
-        uint64_t one = 1, stride = len;
-        const uint8_t *din = call.d_in;
-        uint8_t *dout = call.d_out;
-        ScanState *sst = call.st;
-        void *args[] = {&g, &din, &dout, &one, &stride, &sst, &ent, &plan};
         const void *fn = nullptr;
         switch (g.bpp) {
         case 1: fn = (const void *)k_unfilter<1>; break;
@@ -1509,8 +1507,24 @@ int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, u
         // always the same value for a given instantiation: concurrent callers cannot shrink each other's limit
         const size_t smem = (size_t)UF_WARPS * uf_warp_words((int)g.bpp) * sizeof(uint32_t);
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            e = cudaLaunchCooperativeKernel(fn, dim3(g.n_pass * plan.ctas_per_item), dim3(UF_WARPS * 32), args, smem, call.stream);
+        int per_sm = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, UF_WARPS * 32, smem);
+        if (e != cudaSuccess || per_sm < 1) return fail_cuda(e, "k_unfilter occupancy");
+        // The tiles of an (image, pass) item wait on each other across CTAs: a cooperative launch guarantees that the
+        // whole grid is resident even when other streams keep the device busy.  One image: one CTA per SM (one pipeline
+        // warp per scheduler).  A batch: as many CTA groups as fit, each walking its share of the items.
+        const uint32_t capacity = (uint32_t)per_sm * (uint32_t)call.c->num_sms;
+        const uint64_t n_items = (uint64_t)n_images * g.n_pass;
+        const uint32_t want = (max_tiles + UF_WARPS - 1) / UF_WARPS;
+        const uint32_t room = n_items == 1 ? (uint32_t)call.c->num_sms : capacity;
+        plan.ctas_per_item = std::max(1u, std::min(want, n_items <= g.n_pass ? room / g.n_pass : room));
+        const uint32_t groups = (uint32_t)std::min<uint64_t>(n_items, std::max(1u, capacity / plan.ctas_per_item));
+        uint64_t n = n_images, stride = len;
+        const uint8_t *din = call.d_in;
+        uint8_t *dout = call.d_out;
+        ScanState *sst = call.st;
+        void *args[] = {&g, &din, &dout, &n, &stride, &sst, &ent, &plan};
+        e = cudaLaunchCooperativeKernel(fn, dim3(groups * plan.ctas_per_item), dim3(UF_WARPS * 32), args, smem, call.stream);
         if (e != cudaSuccess) return fail_cuda(e, "cudaLaunchCooperativeKernel(k_unfilter)");
     }
     if (int rc = call.check("k_unfilter")) return rc;
@@ -1523,9 +1537,16 @@ int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, u
     }
 #endif
     if (st.fail) return fail(OXI_E_DATA, "invalid filter type byte (PngError::InvalidData)");
-    if (int rc = call.download(out, g.data_len)) return rc;
+    if (int rc = call.download(out, (size_t)g.data_len * n_images)) return rc;
     if (out_len) *out_len = g.data_len;
     return OXI_OK;
+}
+
+int oxi_unfilter_image(const oxi_ihdr *h, const uint8_t *filtered, size_t len, uint8_t *out, size_t *out_len) {
+    return unfilter_streams(h, filtered, len, 1, out, out_len);
+}
+int oxi_unfilter_batch(const oxi_ihdr *h, const uint8_t *filtered, size_t len, size_t n_images, uint8_t *out, size_t *out_len) {
+    return unfilter_streams(h, filtered, len, n_images, out, out_len);
 }
 
 int oxi_cooccurrence_build(const oxi_ihdr *h, uint32_t n, const uint8_t *data, size_t len, uint32_t *matrix) {

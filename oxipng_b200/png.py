@@ -299,6 +299,39 @@ def unfilter_image_device(ihdr: IhdrData, d_filtered: int, length: int, d_out: i
     return n.value
 
 
+def unfilter_batch(ihdr: IhdrData, filtered) -> np.ndarray:
+    """oxi_unfilter_batch: filtered = (n_images, len) array of inflated streams of identical IHDR -> (n_images, data_len)."""
+    f = np.ascontiguousarray(filtered, dtype=np.uint8)
+    assert f.ndim == 2
+    n_images, length = f.shape
+    h = ihdr._c()
+    out = np.empty(f.size + 16, dtype=np.uint8)
+    n = C.c_size_t(0)
+    L = lib()
+    L.oxi_unfilter_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
+    rc = L.oxi_unfilter_batch(C.byref(h), C.c_void_p(f.ctypes.data), length, n_images, C.c_void_p(out.ctypes.data), C.byref(n))
+    if rc == -5:
+        raise ValueError("invalid filter type byte")
+    check(rc, "oxi_unfilter_batch")
+    return out[:n.value * n_images].reshape(n_images, n.value)
+
+
+def unfilter_batch_device(ihdr: IhdrData, d_filtered: int, length: int, n_images: int, d_out: int, device: int = 0,
+                          stream: int = 0) -> int:
+    """oxi_unfilter_batch_device: device pointers in and out; returns the bytes per image written to d_out."""
+    h = ihdr._c()
+    n = C.c_size_t(0)
+    L = lib()
+    L.oxi_unfilter_batch_device.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                            C.c_void_p]
+    rc = L.oxi_unfilter_batch_device(device, C.c_void_p(stream), C.byref(h), C.c_void_p(d_filtered), length, n_images,
+                                     C.c_void_p(d_out), C.byref(n))
+    if rc == -5:
+        raise ValueError("invalid filter type byte")
+    check(rc, "oxi_unfilter_batch_device")
+    return n.value
+
+
 def interlace_image(png: PngImage) -> PngImage:
     """interlace_image (interlace.rs:6-60): progressive -> Adam7 layout."""
     h = png.ihdr._c()

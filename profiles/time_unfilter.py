@@ -57,6 +57,33 @@ def main():
         res[name] = {'ms': round(ms, 4), 'algorithmic_GBps': round(alg / ms / 1e6, 1), 'frac': round(alg / ms / 1e6 / PEAK, 4),
                      'parity': ok, 'filter_mix': mix}
         print(name, res[name], flush=True)
+    for name, (w, h, ch, bd, n) in [('batch_256x_rgba8_1024_minsum', (1024, 1024, 4, 8, 256)), ('batch_64x_rgb8_2048_minsum', (2048, 2048, 3, 8, 64))]:
+        if only and name not in only:
+            continue
+        ct = {1: ox.ColorType.Grayscale(), 3: ox.ColorType.RGB(), 4: ox.ColorType.RGBA()}[ch]
+        hdr = ox.IhdrData(w, h, ct, ox.BitDepth(bd))
+        d = synth.photo_batch(n, w, h, ch, bd, 1, dev)
+        per = d.numel() // n
+        outs = ox.filter_batch(hdr, d.cpu().numpy(), n, [ox.FilterStrategy.MinSum], False)[0][0]
+        f = torch.from_numpy(np.ascontiguousarray(outs)).to(dev).reshape(-1)
+        flen = f.numel() // n
+        fin = torch.cat([f, torch.zeros(64, dtype=torch.uint8, device=dev)])
+        o = torch.empty(d.numel() + 64, dtype=torch.uint8, device=dev)
+        ts = []
+        for it in range(8):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            m = ox.unfilter_batch_device(hdr, fin.data_ptr(), flen, n, o.data_ptr(), 0, stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ok = bool(m == per and torch.equal(o[:d.numel()], d))
+        ms = statistics.median(ts[2:])
+        alg = 2 * d.numel() + h * n
+        res[name] = {'ms': round(ms, 4), 'algorithmic_GBps': round(alg / ms / 1e6, 1), 'frac': round(alg / ms / 1e6 / PEAK, 4),
+                     'parity': ok, 'images_per_s': round(n / ms * 1e3)}
+        print(name, res[name], flush=True)
     if not only:
         json.dump(res, open('/root/repo/gpurun_out/unfilter_times.json', 'w'), indent=1)
 

@@ -63,6 +63,24 @@ def test_unfilter_tile_pipeline_tall_images():
         assert np.array_equal(ox.unfilter_image(helpers.product_image(il_ih, il_d).ihdr, filtered), il_d), (ct, bd, w, h)
 
 
+def test_unfilter_batch_equals_single_images():
+    """oxi_unfilter_batch: many streams of one IHDR in one launch (more items than CTA groups) == image by image"""
+    import oxipng_b200 as ox
+    for ct, bd, w, h, il, n in [(6, 8, 61, 70, False, 700), (2, 8, 33, 45, True, 90), (0, 16, 20, 33, False, 40), (6, 16, 17, 40, False, 25)]:
+        streams, datas = [], []
+        for i in range(n):
+            ih, d = helpers.synth_image(w, h, ct, bd, 100 + i, "photo" if i % 3 else "random", il)
+            kind = [oracle.MINSUM, oracle.ENTROPY, oracle.BIGRAMS][i % 3]
+            filtered, _, _ = oracle.filter_image(ih, d, kind, 0)
+            streams.append(filtered)
+            datas.append(d)
+        hdr = helpers.product_image(ih, d).ihdr
+        got = ox.unfilter_batch(hdr, np.stack(streams))
+        assert got.shape == (n, datas[0].size)
+        for i in range(n):
+            assert np.array_equal(got[i], datas[i]), (ct, bd, w, h, il, i)
+
+
 def test_unfilter_golden_fixtures(golden):
     """the reference's own files: stream as stored in the PNG (whatever filters its encoder chose) -> pixels"""
     import oxipng_b200 as ox
