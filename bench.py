@@ -370,6 +370,7 @@ def run_ours(args):
         others = {}
         for part, fn in (("single", lambda: bx.single_image_configs(ox, synth, torch, dev, local, stream, peak_gbs, it)),
                          ("batch", lambda: bx.batch_configs(ox, synth, torch, dev, local, stream, peak_gbs, it)),
+                         ("unfilter", lambda: bx.unfilter_configs(ox, synth, torch, np, dev, local, stream, peak_gbs, it)),
                          ("c4", lambda: {"c4_reductions_2048_256colours": bx.c4_reductions(ox, torch, dev, local, stream, peak_gbs)}),
                          ("o2", lambda: {"o2_flow_resident_2048_256colours": bx.o2_flow(ox, torch, dev, local, stream)})):
             try:

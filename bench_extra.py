@@ -201,6 +201,43 @@ def batch_configs(ox, synth, torch, dev, local, stream, peak, iters, n_images=25
     return res
 
 
+def unfilter_configs(ox, synth, torch, np, dev, local, stream, peak, iters):
+    """SURVEY 8f row 1 (PngImage::new -> unfilter_image, png/mod.rs:335-351): the filtered stream of a MinSum search back to
+    pixels, device resident (oxi_unfilter_image_device / oxi_unfilter_batch_device), L2 flushed between iterations.
+    Algorithmic bytes 2N + S.  parity = the rebuilt pixels equal the image the stream was made from.  One image is a
+    dependency chain of width + height pixels (latency-bound); a batch fills the device with independent chains."""
+    S = ox.FilterStrategy
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    res = {}
+    cases = [("unfilter_rgba8_4096_minsum_stream", 4096, 4096, 4, 8, 1, S.MinSum),
+             ("unfilter_rgba8_4096_all_paeth_stream", 4096, 4096, 4, 8, 1, S.PAETH),
+             ("unfilter_rgb8_8192_minsum_stream", 8192, 8192, 3, 8, 1, S.MinSum),
+             ("unfilter_batch_256x_rgba8_1024_minsum_streams", 1024, 1024, 4, 8, 256, S.MinSum)]
+    for name, w, h, ch, bd, n, strat in cases:
+        ct = {3: ox.ColorType.RGB(), 4: ox.ColorType.RGBA()}[ch]
+        hdr = ox.IhdrData(w, h, ct, ox.BitDepth(bd))
+        d = synth.photo_batch(n, w, h, ch, bd, 1, dev)
+        per = d.numel() // n
+        rows = h
+        f = torch.empty(n * (per + rows) + 64, dtype=torch.uint8, device=dev)
+        used = torch.empty(n * rows, dtype=torch.uint8, device=dev)
+        ox.filter_batch_device(local, stream.cuda_stream, hdr, d.data_ptr(), per, n, [strat], False, [f.data_ptr()], [used.data_ptr()])
+        torch.cuda.synchronize()
+        o = torch.empty(d.numel() + 64, dtype=torch.uint8, device=dev)
+        got = [0]
+
+        def step():
+            got[0] = ox.unfilter_batch_device(hdr, f.data_ptr(), per + rows, n, o.data_ptr(), local, stream.cuda_stream)
+        ms = time_kernel(step, stream, torch, flush, iters)
+        ok = bool(got[0] == per and torch.equal(o[:d.numel()], d))
+        alg = 2 * d.numel() + rows * n
+        res[name] = {"ms": ms, "algorithmic_MB": alg / 1e6, "algorithmic_GBps": alg / ms / 1e6, "frac": alg / ms / 1e6 / peak,
+                     "parity": ok, "images_per_s": n / ms * 1e3,
+                     "filter_mix": np.bincount(used.cpu().numpy(), minlength=5).tolist()}
+        del d, f, o
+    return res
+
+
 def c4_images(helpers, R, np):
     rng = np.random.default_rng(0xB2000004)
     pal = rng.integers(0, 256, size=(256, 4), dtype=np.uint8)

@@ -602,16 +602,36 @@ __global__ void __launch_bounds__(RT) k_deinterlace(const uint8_t *__restrict__ 
 // c+1 and stores row j of chunk c-1 (double-buffered windows and result arrays, branch-free: rows and pixels that do
 // not exist are clipped by one unsigned compare on tile-relative 32-bit offsets), so a lone warp per scheduler has
 // independent work to issue while the dependency chain of the step waits.
-constexpr int UF_WARPS = 4, UF_RAW = 33, UF_SUB = 8, UF_AHEAD = 1;
+constexpr int UF_WARPS = 4, UF_RAW = 33, UF_SUB = 8, UF_RING = 64;
 // per-warp shared memory, in words: two windows x 32 rows, two result buffers of one or two [32][CH+1] arrays
 constexpr int uf_warp_words(int bpp) { return 2 * 32 * UF_RAW + 2 * (bpp > 4 ? 2 * 32 * 17 : 32 * 33); }
 constexpr uint32_t UF_MAX_ROW = 1u << 24; // tile-relative offsets are 32-bit: rows of 16 MB and more are refused
+
+// Shared-memory mailbox between the CTA's four pipeline warps and its poller warp.  Polling the boundary words from a
+// pipeline warp costs it one exposed L2 round trip per sub-chunk (its loads queue behind its own stores and copies:
+// measured 224 instead of 121 cycles per step, whatever the prefetch distance); the poller warp does nothing else, keeps
+// 32 words per pipeline warp in flight and hands the pixels over through a small ring, so a pipeline warp only ever
+// waits on shared memory.
+struct UfSlot {
+    unsigned long long ent;   // request: boundary words of the tile above (second array: + ent_words)
+    uint32_t npix, tag;       // request: pixels per row, expected tag
+    uint32_t gen;             // request number, bumped last (0 = none yet)
+    uint32_t avail;           // poller -> pipeline warp: pixels [0, avail) of the boundary row are in the ring
+    uint32_t cons;            // pipeline warp -> poller: pixels [0, cons) have been taken out of the ring
+    uint32_t pad_;
+    uint32_t ring0[UF_RING], ring1[UF_RING];
+};
+struct UfCtl {
+    UfSlot slot[UF_WARPS];
+    uint32_t done; // pipeline warps that have finished all their items
+};
 
 struct UfPlan {
     uint64_t ent_base[7]; // first boundary word of each pass (tile t of pass p: ent_base[p] + t * pixels)
     uint64_t ent_words;   // words per boundary array of one image
     uint32_t ent_arrays;  // 1, or 2 for 6/8-byte pixels (second pixel word)
     uint32_t ctas_per_item;
+    uint32_t backoff_ns;  // poller sleep after a round without progress (batches: several CTAs share an SM's issue slots)
 };
 
 __device__ __forceinline__ uint32_t vadd4_keep(uint32_t d, uint32_t p, uint32_t keep) { // (d + p) per byte, & keep
@@ -626,7 +646,7 @@ __device__ __forceinline__ unsigned long long ld_entry(const unsigned long long 
 // Stores of the step loop are written as global-space asm WITHOUT a memory clobber: nothing in this thread reads them
 // back, and a generic store (or a clobber) would pin every shared-memory load of the unrolled steps behind it.
 __device__ __forceinline__ void st_entry(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v));
+    asm volatile("st.global.u64 [%0], %1;" ::"l"(p), "l"(v));
 }
 __device__ __forceinline__ void stg8(uint8_t *p, uint32_t v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v)); }
 __device__ __forceinline__ void stg16(uint8_t *p, uint32_t v) { asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v)); }
@@ -659,6 +679,8 @@ struct UfTile {
     uint32_t len, npix, delta, maxd, lastlane, tag;
     uint32_t m1, m2, m3, m4;
     bool valid, dep, pub;
+    UfSlot *slot;  // this warp's mailbox
+    uint32_t gen;  // request number of this tile (dep tiles)
 };
 
 // MODE 0: None/Sub/Up rows only; 1: + Average; 2: + Paeth
@@ -682,7 +704,6 @@ __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t
     const ptrdiff_t lo_d = T.in_lo - T.src0, hi_d = T.in_hi - T.src0;
     const int lo_rel = lo_d < -(ptrdiff_t)(1 << 29) ? -(1 << 29) : (int)lo_d;
     const int hi_rel = hi_d > (ptrdiff_t)0x7fffffff ? 0x7fffffff : (int)hi_d;
-    const unsigned long long want = T.tag; // tag of tile t-1's words = t (its index + 1)
     const bool publane = T.pub && lane == T.lastlane;
 
     // row r's words of a chunk -> its window; lanes = consecutive words of that row.  win_s: shared address of this
@@ -702,21 +723,19 @@ __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t
     const int st_row = CH == 16 ? (int)(lane & 16u) : 0, st_px = CH == 16 ? (int)(lane & 15u) : (int)lane;
 
     uint32_t l0 = 0, l1 = 0, ul0 = 0, ul1 = 0; // rebuilt left pixel, upleft pixel
-    // boundary words of the current sub-chunk (c0/c1, lanes 0..UF_SUB-1) and of the next UF_AHEAD ones: a word is
-    // requested UF_AHEAD sub-chunks before its use (an L2 round trip is several steps long) and re-polled at its use
-    // only if its tag was still missing then
-    unsigned long long c0 = 0, c1 = 0, e0[UF_AHEAD] = {}, e1[UF_AHEAD] = {};
-    if (T.dep && lane < UF_SUB) {
-        if (lane < T.npix) {
-            c0 = ld_entry(T.ent_in + lane);
-            if (N1) c1 = ld_entry(T.ent_in + T.ent_words + lane);
+    // boundary pixels of the current sub-chunk (lanes 0..UF_SUB-1), taken from the mailbox ring
+    uint32_t c0 = 0, c1 = 0;
+    volatile UfSlot *slot = T.slot;
+    if (T.dep) { // post the request; the poller starts on it when it sees the new request number
+        if (lane == 0) {
+            slot->ent = (unsigned long long)reinterpret_cast<uintptr_t>(T.ent_in);
+            slot->npix = T.npix;
+            slot->tag = T.tag;
+            slot->avail = 0;
+            slot->cons = 0;
+            __threadfence_block();
+            slot->gen = T.gen;
         }
-#pragma unroll
-        for (int a = 0; a + 1 < UF_AHEAD; a++)
-            if (lane + (a + 1) * UF_SUB < T.npix) {
-                e0[a] = ld_entry(T.ent_in + lane + (a + 1) * UF_SUB);
-                if (N1) e1[a] = ld_entry(T.ent_in + T.ent_words + lane + (a + 1) * UF_SUB);
-            }
     }
     __syncwarp();
 #pragma unroll 4
@@ -737,22 +756,18 @@ __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t
 #pragma unroll
         for (int q = 0; q < CH / UF_SUB; q++) {
             if (T.dep) {
-                const uint32_t xs = c * CH + q * UF_SUB + lane; // lane 0's row is at delta 0: step == pixel
-                for (;;) {
-                    const bool ok = lane >= UF_SUB || xs >= T.npix ||
-                                    ((c0 >> 32) == want && (!N1 || (c1 >> 32) == want));
-                    if (__all_sync(0xffffffffu, ok)) break;
-                    if (!ok) {
-                        c0 = ld_entry(T.ent_in + xs);
-                        if (N1) c1 = ld_entry(T.ent_in + T.ent_words + xs);
+                const uint32_t xb = c * CH + q * UF_SUB; // lane 0's row is at delta 0: step == pixel
+                if (xb < T.npix) {
+                    const uint32_t need = min(xb + UF_SUB, T.npix);
+                    while (slot->avail < need) {}
+                    // (no fence: the ring words were written before `avail` by the same warp, and a warp's volatile
+                    // shared-memory accesses are performed in program order)
+                    if (lane < UF_SUB) {
+                        c0 = slot->ring0[(xb + lane) & (UF_RING - 1)];
+                        if (N1) c1 = slot->ring1[(xb + lane) & (UF_RING - 1)];
                     }
-                }
-                // requested only now, AFTER the check: the check waits on the scoreboard these loads share, so a
-                // request issued in front of it would be waited for as well (measured: one exposed L2 round trip per
-                // sub-chunk, 224 instead of 121 cycles per step)
-                if (lane < UF_SUB && xs + UF_AHEAD * UF_SUB < T.npix) {
-                    e0[UF_AHEAD - 1] = ld_entry(T.ent_in + xs + UF_AHEAD * UF_SUB);
-                    if (N1) e1[UF_AHEAD - 1] = ld_entry(T.ent_in + T.ent_words + xs + UF_AHEAD * UF_SUB);
+                    __syncwarp();
+                    if (lane == 0) slot->cons = need;
                 }
             }
             // every shared-memory read of the sub-chunk up front (ptxas keeps LDS behind an earlier LDGSTS, so a load
@@ -776,8 +791,8 @@ __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t
                 // pixel above: lane l-1's result of the previous step; lane 0: the boundary word
                 uint32_t a0 = __shfl_up_sync(0xffffffffu, l0, 1);
                 uint32_t a1 = N1 ? __shfl_up_sync(0xffffffffu, l1, 1) : 0u;
-                const uint32_t b0 = __shfl_sync(0xffffffffu, (uint32_t)c0, jj);
-                const uint32_t b1 = N1 ? __shfl_sync(0xffffffffu, (uint32_t)c1, jj) : 0u;
+                const uint32_t b0 = __shfl_sync(0xffffffffu, c0, jj);
+                const uint32_t b1 = N1 ? __shfl_sync(0xffffffffu, c1, jj) : 0u;
                 if (lane == 0) { a0 = b0; a1 = b1; }
                 const int x = x0 + j;
                 const bool act = T.valid && (uint32_t)x < T.npix;
@@ -802,16 +817,17 @@ __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t
                     if (N1) st_entry(T.ent_out + T.ent_words + x, ((unsigned long long)(T.tag + 1) << 32) | l1);
                 }
                 // off the chain: next chunk's row(s) in, previous chunk's row(s) out
+#ifndef UF_EXP_NOFETCH
                 fetch_row(next_s, next_add, j);
                 if (CH == 16) fetch_row(next_s, next_add, j + 16);
+#endif
                 const int rr = j + st_row;
                 const int pos = __shfl_sync(0xffffffffu, dstoff, rr) + st_add;
+#ifndef UF_EXP_NOSTORE
                 if ((uint32_t)(pos - rr * (int)T.len) < T.len) st_pixel<BPP>(T.dst0 + pos, s0[jj], s1[jj]);
-            }
-            if (T.dep) {
-                c0 = e0[0]; c1 = e1[0];
-#pragma unroll
-                for (int a = 0; a + 1 < UF_AHEAD; a++) { e0[a] = e0[a + 1]; e1[a] = e1[a + 1]; }
+#else
+                if ((uint32_t)(pos - rr * (int)T.len) < T.len && s0[jj] == 0x12345678u) st_pixel<BPP>(T.dst0 + pos, s0[jj], s1[jj]);
+#endif
             }
         }
     }
@@ -819,8 +835,61 @@ __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t
     __syncwarp();
 }
 
+// the CTA's poller warp: see UfSlot
 template <int BPP>
-__global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_t *__restrict__ in, uint8_t *out,
+__device__ __noinline__ void uf_poller(volatile UfCtl *ctl, const uint64_t ent_words, const uint32_t backoff_ns, const uint32_t lane) {
+    constexpr bool N1 = BPP > 4;
+    uint32_t mygen[UF_WARPS] = {}, myavail[UF_WARPS] = {}, npix[UF_WARPS] = {}, tag[UF_WARPS] = {};
+    const unsigned long long *ptr[UF_WARPS] = {};
+    for (;;) {
+        if (ctl->done >= (uint32_t)UF_WARPS) break;
+        unsigned long long e0[UF_WARPS], e1[UF_WARPS];
+        bool want[UF_WARPS], progress = false;
+#pragma unroll
+        for (int w = 0; w < UF_WARPS; w++) { // all requests first: the loads of the four mailboxes overlap
+            volatile UfSlot *sl = &ctl->slot[w];
+            const uint32_t g = sl->gen;
+            if (g != mygen[w]) {
+                __threadfence_block();
+                ptr[w] = reinterpret_cast<const unsigned long long *>((uintptr_t)sl->ent);
+                npix[w] = sl->npix;
+                tag[w] = sl->tag;
+                mygen[w] = g;
+                myavail[w] = 0;
+            }
+            const uint32_t limit = min(npix[w], sl->cons + (uint32_t)UF_RING);
+            const uint32_t x = myavail[w] + lane;
+            want[w] = mygen[w] != 0 && x < limit;
+            e0[w] = 0; e1[w] = 0;
+            if (want[w]) {
+                e0[w] = ld_entry(ptr[w] + x);
+                if (N1) e1[w] = ld_entry(ptr[w] + ent_words + x);
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < UF_WARPS; w++) {
+            volatile UfSlot *sl = &ctl->slot[w];
+            const bool ok = want[w] && (uint32_t)(e0[w] >> 32) == tag[w] && (!N1 || (uint32_t)(e1[w] >> 32) == tag[w]);
+            const uint32_t nb = __ballot_sync(0xffffffffu, ok);
+            const uint32_t n = nb == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~nb) - 1u; // leading run of valid words
+            if (n == 0) continue;
+            const uint32_t x = myavail[w] + lane;
+            if (lane < n) {
+                sl->ring0[x & (UF_RING - 1)] = (uint32_t)e0[w];
+                if (N1) sl->ring1[x & (UF_RING - 1)] = (uint32_t)e1[w];
+            }
+            __syncwarp();
+            __threadfence_block();
+            myavail[w] += n;
+            if (lane == 0) sl->avail = myavail[w];
+            progress = true;
+        }
+        if (backoff_ns && !progress) __nanosleep(backoff_ns);
+    }
+}
+
+template <int BPP>
+__global__ void __launch_bounds__((UF_WARPS + 1) * 32) k_unfilter(Geom g, const uint8_t *__restrict__ in, uint8_t *out,
                                                             uint64_t n_images, uint64_t in_stride, ScanState *st,
                                                             unsigned long long *ent, UfPlan plan) {
     extern __shared__ __align__(16) uint32_t uf_smem[];
@@ -831,6 +900,14 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
     const uint32_t group = blockIdx.x / plan.ctas_per_item, ngroups = gridDim.x / plan.ctas_per_item;
     const uint32_t gw = (blockIdx.x % plan.ctas_per_item) * UF_WARPS + warp, NW = plan.ctas_per_item * UF_WARPS;
     if (group >= ngroups) return;
+    UfCtl *ctl = reinterpret_cast<UfCtl *>(uf_smem + UF_WARPS * uf_warp_words(BPP));
+    for (uint32_t i = threadIdx.x; i < sizeof(UfCtl) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(ctl)[i] = 0;
+    __syncthreads();
+    if (warp == UF_WARPS) { // the poller warp
+        uf_poller<BPP>(ctl, plan.ent_words, plan.backoff_ns, lane);
+        return;
+    }
+    uint32_t mygen = 0;
     for (uint64_t item = group; item < n_images * g.n_pass; item += ngroups) {
     const uint64_t img = item / g.n_pass;
     const uint32_t pass = (uint32_t)(item % g.n_pass);
@@ -864,6 +941,9 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
         T.pub = t + 1 < ntiles;
         T.lastlane = min(31u, pd.nrows - 1u - t * 32u);
         T.tag = t;
+        T.slot = &ctl->slot[warp];
+        if (T.dep) mygen++;
+        T.gen = mygen;
         T.ent_out = ebase + (uint64_t)t * npix;
         T.ent_in = ebase + (uint64_t)(t ? t - 1 : 0) * npix;
         const bool any_avg = __any_sync(0xffffffffu, f == 3), any_paeth = __any_sync(0xffffffffu, f == 4);
@@ -880,6 +960,8 @@ __global__ void __launch_bounds__(UF_WARPS * 32) k_unfilter(Geom g, const uint8_
 #endif
     }
     }
+    __syncwarp();
+    if (lane == 0) atomicAdd(&ctl->done, 1u);
 }
 
 // ---- host-side call scaffolding -------------------------------------------------------------------------------------------
@@ -1505,10 +1587,10 @@ static int unfilter_streams(const oxi_ihdr *h, const uint8_t *filtered, size_t l
         default: return fail(OXI_E_ARG, "unsupported filter bpp");
         }
         // always the same value for a given instantiation: concurrent callers cannot shrink each other's limit
-        const size_t smem = (size_t)UF_WARPS * uf_warp_words((int)g.bpp) * sizeof(uint32_t);
+        const size_t smem = (size_t)UF_WARPS * uf_warp_words((int)g.bpp) * sizeof(uint32_t) + sizeof(UfCtl);
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, UF_WARPS * 32, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (UF_WARPS + 1) * 32, smem);
         if (e != cudaSuccess || per_sm < 1) return fail_cuda(e, "k_unfilter occupancy");
         // The tiles of an (image, pass) item wait on each other across CTAs: a cooperative launch guarantees that the
         // whole grid is resident even when other streams keep the device busy.  One image: one CTA per SM (one pipeline
@@ -1519,12 +1601,13 @@ static int unfilter_streams(const oxi_ihdr *h, const uint8_t *filtered, size_t l
         const uint32_t room = n_items == 1 ? (uint32_t)call.c->num_sms : capacity;
         plan.ctas_per_item = std::max(1u, std::min(want, n_items <= g.n_pass ? room / g.n_pass : room));
         const uint32_t groups = (uint32_t)std::min<uint64_t>(n_items, std::max(1u, capacity / plan.ctas_per_item));
+        plan.backoff_ns = groups > g.n_pass ? 500u : 0u;
         uint64_t n = n_images, stride = len;
         const uint8_t *din = call.d_in;
         uint8_t *dout = call.d_out;
         ScanState *sst = call.st;
         void *args[] = {&g, &din, &dout, &n, &stride, &sst, &ent, &plan};
-        e = cudaLaunchCooperativeKernel(fn, dim3(groups * plan.ctas_per_item), dim3(UF_WARPS * 32), args, smem, call.stream);
+        e = cudaLaunchCooperativeKernel(fn, dim3(groups * plan.ctas_per_item), dim3((UF_WARPS + 1) * 32), args, smem, call.stream);
         if (e != cudaSuccess) return fail_cuda(e, "cudaLaunchCooperativeKernel(k_unfilter)");
     }
     if (int rc = call.check("k_unfilter")) return rc;
