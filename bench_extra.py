@@ -232,7 +232,7 @@ def unfilter_configs(ox, synth, torch, np, dev, local, stream, peak, iters):
         ok = bool(got[0] == per and torch.equal(o[:d.numel()], d))
         alg = 2 * d.numel() + rows * n
         res[name] = {"ms": ms, "algorithmic_MB": alg / 1e6, "algorithmic_GBps": alg / ms / 1e6, "frac": alg / ms / 1e6 / peak,
-                     "parity": ok, "images_per_s": n / ms * 1e3,
+                     "parity": ok, "images_per_s": n / ms * 1e3, "raw_pixel_GBps": d.numel() / ms / 1e6,
                      "filter_mix": np.bincount(used.cpu().numpy(), minlength=5).tolist()}
         del d, f, o
     return res

@@ -555,7 +555,7 @@ using namespace oxi;
 extern "C" {
 
 const char *oxi_last_error(void) { return t_err.c_str(); }
-const char *oxi_version(void) { return "oxipng-b200 0.2.0 (sm_100a)"; }
+const char *oxi_version(void) { return "oxipng-b200 0.3.0 (sm_100a)"; }
 int oxi_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

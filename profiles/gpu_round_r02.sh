@@ -19,3 +19,7 @@ for cfg in c5 c3a c1 c2 o2 alpha; do
 done
 python profiles/line_profile.py gpurun_out/${tag}_c5_full.ncu-rep oxipng_b200/liboxipng_b200.so k_fastILi1ELi12E 60 > gpurun_out/${tag}_c5_line_profile.txt 2>&1
 python profiles/launch_list.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_launch_list.txt 2>&1
+# unfilter_image (single images and a batch), then full captures of two single-image cases
+python profiles/time_unfilter.py > gpurun_out/${tag}_unfilter_times.txt 2>&1; echo "unfilter times exit $?"
+cp gpurun_out/unfilter_times.json gpurun_out/${tag}_unfilter_times.json 2>/dev/null
+bash profiles/ncu_unfilter.sh ${tag}_unfilter rgba8_4096_minsum rgba8_4096_all_paeth

@@ -23,6 +23,8 @@ def r1_of(name):
          "c3a_bigrams_rgba16_4096": "c3a_bigrams_rgba16_4096", "c3a_bigent_rgba16_4096": "c3a_bigent_rgba16_4096",
          "c3b_bigrams_bigent_rgba8_4096_adam7": "c3b_bigrams_bigent_rgba8_4096_adam7",
          "bigrams_bigent_rgba8_4096": "bigrams_bigent_rgba8_4096"}.get(name)
+    if name == "unfilter_rgba8_4096_minsum_stream":
+        return "7.7 ms / 0.27 % (ncu, r1 kernel)"
     v = r1oc.get(m) if m else None
     return f"{v['ms']:.4f} ms / {pct(v['frac_of_measured_hbm'])}" if v else "–"
 
@@ -36,7 +38,7 @@ out.append(f"| **c5: 1250 × 1024² RGBA8, {{None,Bigrams,BigEnt}} fused** (`val
 for k, v in oc.items():
     if not isinstance(v, dict) or "ms" not in v or "frac" not in v or k.startswith("o2_flow"):
         continue
-    raw = f"{v['raw_pixel_GBps']:.0f} GB/s" + (f", {v['images_per_s'] / 1e3:.1f} k images/s" if "images_per_s" in v else "")
+    raw = f"{v.get('raw_pixel_GBps', v.get('algorithmic_GBps', 0) / 2):.0f} GB/s" + (f", {v['images_per_s'] / 1e3:.1f} k images/s" if "images_per_s" in v and not (k.startswith("unfilter_") and "batch" not in k) else "")
     out.append(f"| `{k}`{' (' + v['tier'] + ' tier)' if v.get('tier') else ''} | {v['ms']:.4f} ms | {raw} | {pct(v['frac'])} | {v['parity']} | {r1_of(k)} |")
 out.append("")
 c4 = oc.get("c4_reductions_2048_256colours", {})
@@ -80,9 +82,9 @@ if os.environ.get("README"):
     o = oc
     n2 = more[0] if more else None
     lines = ["| What | Result |", "|---|---|",
-             "| Parity | bit-exact vs the CPU oracle through the C ABI (72 GPU tests): 68 reference fixtures × 9 strategies × alpha on/off, ragged / interlaced / sub-byte / 16-bit images, eight whole c5 images (clean, noisy, random), the split-table / wide-table / Entropy+Bigrams kernels, the `optimize_alpha` tier, all reductions host-buffer and resident, the resident `-o2` flow, row-band sharding, 12 threads × mixed geometries. The oracle itself is pinned against PIL/OpenCV decodes of 243 reference fixtures — **not** against the real oxipng (no Rust toolchain here; `tools/ref_dump.rs` closes that gap where cargo exists) |",
+             "| Parity | bit-exact vs the CPU oracle through the C ABI (74 GPU tests): 68 reference fixtures × 9 strategies × alpha on/off, ragged / interlaced / sub-byte / 16-bit images, eight whole c5 images (clean, noisy, random), the split-table / wide-table / Entropy+Bigrams kernels, the `optimize_alpha` tier, all reductions host-buffer and resident, the resident `-o2` flow, row-band sharding, 12 threads × mixed geometries. The oracle itself is pinned against PIL/OpenCV decodes of 243 reference fixtures — **not** against the real oxipng (no Rust toolchain here; `tools/ref_dump.rs` closes that gap where cargo exists) |",
              f"| c5: 1250 × 1024² RGBA8, {{None, Bigrams, BigEnt}} fused, one GPU | **{d['ms_per_step']:.1f} ms = {d['value']:.0f} GB/s raw pixels, {d['images_per_s'] / 1e3:.1f} k images/s** ({pct(d['roofline']['frac'])} of the measured HBM roofline; round 1: {r1['ms_per_step']:.1f} ms, {pct(r1['roofline']['frac'])}); issue / ALU / shared-memory bound, DRAM 10 % |",
-             f"| End to end through `oxi_filter_batch` (host buffers) | {e['value']:.1f} GB/s raw pixels with pinned buffers = the PCIe copy ceiling ({cc['per_rank_GBps']:.0f} GB/s both ways; three filtered streams leave the device per image), {ep['value']:.1f} GB/s with pageable buffers, vs {cpu.get('value', 0):.2f} GB/s for the {cpu.get('cores')}-thread CPU restatement |"]
+             f"| End to end through `oxi_filter_batch` (host buffers) | {e['value']:.1f} GB/s raw pixels with pinned buffers = {100 * cc['e2e_fraction_of_copy_ceiling']:.0f} % of this box's PCIe copy ceiling ({cc['per_rank_GBps']:.0f} GB/s both ways; 95 % on the box of the 2- and 8-GPU records; three filtered streams leave the device per image), {ep['value']:.1f} GB/s with pageable buffers, vs {cpu.get('value', 0):.2f} GB/s for the {cpu.get('cores')}-thread CPU restatement |"]
     if n2:
         rb1, rb2 = d.get("row_band", {}), n2.get("row_band", {})
         lines.append(f"| 2 GPUs | {n2['value']:.0f} GB/s raw pixels ({n2['value'] / d['value']:.2f}×), e2e {n2['e2e']['value']:.1f} GB/s; one 16384² RGBA8 image in row bands, MinSum: {rb1.get('minsum', {}).get('ms', 0):.0f} → {rb2.get('minsum', {}).get('ms', 0):.0f} ms |")
@@ -91,6 +93,9 @@ if os.environ.get("README"):
     lines.append(f"| default `-o2` trial set {{None, Sub, Entropy, Bigrams}}, 256 × 1024² | {o['o2_default_set_none_sub_entropy_bigrams_1024']['ms']:.1f} ms, {o['o2_default_set_none_sub_entropy_bigrams_1024']['images_per_s'] / 1e3:.1f} k images/s (round 1 kernel: 15.0 ms) |")
     lines.append(f"| c5 with ±12 noise on the colour channels | {o['c5_noise12_none_bigrams_bigent_1024']['images_per_s'] / 1e3:.1f} k images/s (round 1 kernel: 8.6 k) |")
     lines.append(f"| `optimize_alpha` on, 10 % transparent blocks | MinSum {o['alpha_optimize_minsum_rgba8_1024_10pct_transparent']['images_per_s'] / 1e3:.1f} k images/s, default set {o['alpha_optimize_o2_set_rgba8_1024_10pct_transparent']['images_per_s'] / 1e3:.1f} k images/s (round 1: 1.7 k / 0.9 k) |")
+    u1, ub = o.get("unfilter_rgba8_4096_minsum_stream"), o.get("unfilter_batch_256x_rgba8_1024_minsum_streams")
+    if u1 and ub:
+        lines.append(f"| `unfilter_image` (decode side), 4096² RGBA8 MinSum stream / batch of 256 × 1024² | {u1['ms']:.2f} ms = {pct(u1['frac'])} of the roofline (round 1: 7.7 ms, 0.27 %) / {ub['ms']:.1f} ms = {pct(ub['frac'])}, {ub['images_per_s'] / 1e3:.0f} k images/s |")
     if fl:
         lines.append(f"| `-o2` reduction stage, 2048² RGBA8 with 256 colours, resident handles | reductions {fl['resident_reductions_ms']:.1f} ms (host buffers {fl['host_buffer_reductions_ms']:.1f} ms, CPU oracle {fl['cpu_oracle_reductions_ms']:.0f} ms); trial fan-out {fl.get('resident_trial_filter_ms', 0):.1f} ms (host buffers {fl.get('host_buffer_trial_filter_ms', 0):.0f} ms, CPU {fl.get('cpu_oracle_trial_filter_ms', 0):.0f} ms) |")
     print("\n@@README@@\n" + "\n".join(lines))
