@@ -57,6 +57,7 @@ struct FastParams {
     uint32_t h0_slots;  // bigram scorer with small_tab: slots of the trial-0 hash table (power of two, > 2 * row bytes)
     const uint8_t *img_class; // optional per-image class written by k_spread_probe (0: residuals within +-16, 1: wider)
     uint32_t want_class;      // the class this launch takes
+    uint32_t four;      // the constant 4, opaque to the compiler (scale4)
     uint32_t small_tab; // bigram scorer: 1 = the dense-table layout (rows <= 16384 bytes), 2 = the split-table layout (<= 32768)
 };
 
@@ -327,31 +328,49 @@ __device__ __forceinline__ void minsum_pass(const uint8_t *cur, const uint8_t *u
 // replaying the lane -> byte map on the c2 image gives 2.14 for that layout and 1.2 for a single copy, because the lanes
 // of one instruction that hold the same residual value then hit the same counter and are merged by the hardware.
 constexpr uint32_t HIST_ADDR = SMEM_WIN + SMEM_HDR; // the histograms are the first thing behind the header in every layout
+// v * four with four == 4 handed in as a kernel parameter: a literal 4 becomes a shift or LEA (ALU pipe), an opaque
+// multiplier stays an IMAD (FMA pipe)
+__device__ __forceinline__ uint32_t scale4(uint32_t v, uint32_t four) {
+    uint32_t d;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(four));
+    return d;
+}
 template <uint32_t HB>
-__device__ __forceinline__ void hist_word(uint32_t r) {
+__device__ __forceinline__ void hist_word(uint32_t r, uint32_t four) {
+#ifdef OXI_HIST_OLD
     const uint32_t lo = (r * 4u) & 0xFCFCFCFCu, hi = (r >> 6) & 0x03030303u;
     smem_inc_at<HB>(prmt(lo, hi, 0xCC40u));
     smem_inc_at<HB>(prmt(lo, hi, 0xDD51u));
     smem_inc_at<HB>(prmt(lo, hi, 0xEE62u));
     smem_inc_at<HB>(prmt(lo, hi, 0xFF73u));
+#else
+    // one PRMT per byte (zero-extended value) on the ALU pipe, the "times four" as IMAD.SHL on the otherwise idle FMA
+    // pipe: the scorer is bound by the ALU pipe (82 % in round 2's capture), and the pre-scaled lo / hi words of the
+    // earlier form cost three more ALU operations per word
+    smem_inc_at<HB>(scale4(prmt(r, 0u, 0x4440u), four));
+    smem_inc_at<HB>(scale4(prmt(r, 0u, 0x4441u), four));
+    smem_inc_at<HB>(scale4(prmt(r, 0u, 0x4442u), four));
+    smem_inc_at<HB>(scale4(prmt(r, 0u, 0x4443u), four));
+#endif
 }
 template <uint32_t HB>
 __device__ __forceinline__ void hist_word_tail(uint32_t r, int nvalid) {
     for (int j = 0; j < nvalid; j++) smem_inc(HB + (((r >> (8 * j)) & 255u) << 2));
 }
 template <int D, bool TAIL>
-__device__ __forceinline__ void entropy_chunk(const uint8_t *cur, const uint8_t *up, uint32_t c, int valid, uint32_t shift) {
+__device__ __forceinline__ void entropy_chunk(const uint8_t *cur, const uint8_t *up, uint32_t c, int valid, uint32_t shift,
+                                              uint32_t four) {
     const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t x = cw.w[k + 2], u = uw.w[k + 2], l = left_word<D>(cw, k, shift), ul = left_word<D>(uw, k, shift);
         const uint32_t r1 = __vsub4(x, l), r2 = __vsub4(x, u), r3 = __vsub4(x, __vhaddu4(l, u)), r4 = __vsub4(x, paeth4(l, u, ul));
         if (!TAIL) {
-            hist_word<HIST_ADDR + 0 * 1024u>(x);
-            hist_word<HIST_ADDR + 1 * 1024u>(r1);
-            hist_word<HIST_ADDR + 2 * 1024u>(r2);
-            hist_word<HIST_ADDR + 3 * 1024u>(r3);
-            hist_word<HIST_ADDR + 4 * 1024u>(r4);
+            hist_word<HIST_ADDR + 0 * 1024u>(x, four);
+            hist_word<HIST_ADDR + 1 * 1024u>(r1, four);
+            hist_word<HIST_ADDR + 2 * 1024u>(r2, four);
+            hist_word<HIST_ADDR + 3 * 1024u>(r3, four);
+            hist_word<HIST_ADDR + 4 * 1024u>(r4, four);
         } else {
             const int nv = min(valid - 4 * k, 4);
             if (nv <= 0) break;
@@ -365,11 +384,11 @@ __device__ __forceinline__ void entropy_chunk(const uint8_t *cur, const uint8_t 
 }
 template <int D, int NT>
 __device__ __forceinline__ void entropy_pass(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
-                                             uint32_t *hist) {
+                                             uint32_t *hist, uint32_t four) {
     static_assert(HIST_REP == 1, "the histogram addressing is written for one copy");
     const uint32_t nfull = len >> 4;
-    for (uint32_t c = threadIdx.x; c < nfull; c += NT) entropy_chunk<D, false>(cur, up, c, 16, shift);
-    if ((len & 15u) && threadIdx.x == (nfull % NT)) entropy_chunk<D, true>(cur, up, nfull, (int)(len & 15u), shift);
+    for (uint32_t c = threadIdx.x; c < nfull; c += NT) entropy_chunk<D, false>(cur, up, c, 16, shift, four);
+    if ((len & 15u) && threadIdx.x == (nfull % NT)) entropy_chunk<D, true>(cur, up, nfull, (int)(len & 15u), shift, four);
 }
 // sum over present values of ilog2i(count) (strategies.rs:136-142); clears the histograms for the next row.
 template <int NT>
@@ -1339,7 +1358,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_WIDE) ? 2 : (SC & SC
                 bool small_flow = false, split_done = false;
                 if (SC & SC_MINSUM) minsum_pass<D, NT>(cur, up, len, shift, sr.s_min_());
                 if (SC & SC_ENTROPY) {
-                    entropy_pass<D, NT>(cur, up, len, shift, sm.hist);
+                    entropy_pass<D, NT>(cur, up, len, shift, sm.hist, P.four);
                     __syncthreads();
                     entropy_score<NT>(sm.hist, sr.s_ent_());
                 }
@@ -1994,6 +2013,7 @@ static cudaError_t launch_fast_variant(const LaunchCtx &ctx, const Geom &g, cons
     P.n_images = n_images;
     P.rb = slot_bytes(g);
     P.shift = 8 * (g.bpp % 4);
+    P.four = 4;
     P.small_tab = split ? 2 : small_tab ? 1 : 0;
     P.h0_slots = small_tab ? h0 : 0;
     P.img_class = img_class;
