@@ -753,7 +753,7 @@ __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t
         const int next_add = (int)((c + 1u) * (CH * BPP)) + 4 * (int)lane;
         const int st_add = ((int)(c * CH) - CH + st_px) * BPP; // chunk c-1 ("-1": nothing passes the range check)
         const int x0 = (int)(c * CH) - (int)T.delta; // this lane's pixel at the chunk's first step
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < CH / UF_SUB; q++) {
             if (T.dep) {
                 const uint32_t xb = c * CH + q * UF_SUB; // lane 0's row is at delta 0: step == pixel
