@@ -817,17 +817,11 @@ __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t
                     if (N1) st_entry(T.ent_out + T.ent_words + x, ((unsigned long long)(T.tag + 1) << 32) | l1);
                 }
                 // off the chain: next chunk's row(s) in, previous chunk's row(s) out
-#ifndef UF_EXP_NOFETCH
                 fetch_row(next_s, next_add, j);
                 if (CH == 16) fetch_row(next_s, next_add, j + 16);
-#endif
                 const int rr = j + st_row;
                 const int pos = __shfl_sync(0xffffffffu, dstoff, rr) + st_add;
-#ifndef UF_EXP_NOSTORE
                 if ((uint32_t)(pos - rr * (int)T.len) < T.len) st_pixel<BPP>(T.dst0 + pos, s0[jj], s1[jj]);
-#else
-                if ((uint32_t)(pos - rr * (int)T.len) < T.len && s0[jj] == 0x12345678u) st_pixel<BPP>(T.dst0 + pos, s0[jj], s1[jj]);
-#endif
             }
         }
     }
