@@ -282,6 +282,11 @@ __host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, uint32_t h0_slots, 
 // it into the reference's score 128*bytes - S_f + f (the filter-type byte f counts |f| = f, png/mod.rs:409-414).
 // S_0 also answers the all-zero-row test: ||x| - 128| is 128 only for x = 0, so S_0 = 128 * bytes iff the row is zero.
 // S0: bpp = 4 (the funnel shift that forms "left" is by zero bits: a plain register pick).
+__device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t acc) { // acc + sum_i |a_i - b_i| (bytes)
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+    return d;
+}
 template <int D, bool TAIL, bool S0>
 __device__ __forceinline__ void minsum_chunk(const uint8_t *cur, const uint8_t *up, uint32_t c, int valid, uint32_t shift,
                                              uint32_t (&a)[5]) {
@@ -296,11 +301,21 @@ __device__ __forceinline__ void minsum_chunk(const uint8_t *cur, const uint8_t *
             const uint32_t m = tail_mask(valid - 4 * k);
             x &= m; u &= m; l &= m; ul &= m;
         }
+#ifdef OXI_MINSUM_OLD
         a[0] = __vsadu4(x, H) + a[0];
         a[1] = __vsadu4(__vabsdiffu4(x, l), H) + a[1];
         a[2] = __vsadu4(__vabsdiffu4(x, u), H) + a[2];
         a[3] = __vsadu4(__vabsdiffu4(x, __vhaddu4(l, u)), H) + a[3];
         a[4] = __vsadu4(__vabsdiffu4(x, paeth4(l, u, ul)), H) + a[4];
+#else
+        // sum of absolute differences straight into the accumulator (VABSDIFF4.ACC with the accumulator as addend): the
+        // compiler's form sums into zero and needs an IADD3 per pair of words on the ALU pipe that bounds this scorer
+        a[0] = sad4_acc(x, H, a[0]);
+        a[1] = sad4_acc(__vabsdiffu4(x, l), H, a[1]);
+        a[2] = sad4_acc(__vabsdiffu4(x, u), H, a[2]);
+        a[3] = sad4_acc(__vabsdiffu4(x, __vhaddu4(l, u)), H, a[3]);
+        a[4] = sad4_acc(__vabsdiffu4(x, paeth4(l, u, ul)), H, a[4]);
+#endif
     }
 }
 template <int D, int NT>
