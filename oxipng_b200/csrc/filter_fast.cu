@@ -337,8 +337,8 @@ __device__ __forceinline__ void minsum_pass(const uint8_t *cur, const uint8_t *u
 }
 
 // Entropy: histogram the residual bytes of all five filters (filter-type byte added at scoring time).  The counter of
-// byte value v of filter f sits at byte offset f*1024 + v*4: low byte (v & 63) << 2, high byte v >> 6, composed per byte by
-// one prmt out of two pre-scaled words; the histogram's shared-window address (+ f*1024) is an immediate of the atomic.
+// byte value v of filter f sits at byte offset f*1024 + v*4: per byte one prmt (v, zero-extended) and one multiply-add
+// (v * 4 + the histogram's shared-window address + f*1024; see scale4), then the atomic.
 // One copy per histogram: round 1 kept four lane-selected, bank-rotated replicas (2.2 wavefronts per ATOMS measured);
 // replaying the lane -> byte map on the c2 image gives 2.14 for that layout and 1.2 for a single copy, because the lanes
 // of one instruction that hold the same residual value then hit the same counter and are merged by the hardware.
