@@ -63,6 +63,25 @@ def test_unfilter_tile_pipeline_tall_images():
         assert np.array_equal(ox.unfilter_image(helpers.product_image(il_ih, il_d).ihdr, filtered), il_d), (ct, bd, w, h)
 
 
+def test_unfilter_wide_rows_and_odd_sizes():
+    """many chunks per row, rows that end inside a chunk / sub-chunk, one-pixel and one-row images, a stream with trailing
+    bytes that do not form a scanline"""
+    import oxipng_b200 as ox
+    rng = np.random.default_rng(9)
+    for ct, bd, w, h in [(6, 8, 5003, 37), (2, 8, 8191, 33), (0, 8, 20001, 5), (6, 16, 3001, 34), (2, 16, 2049, 40),
+                         (4, 8, 4097, 3), (0, 1, 9999, 65), (3, 2, 777, 70), (6, 8, 1, 300), (2, 8, 2, 129), (6, 8, 31, 1),
+                         (6, 8, 33, 32), (6, 8, 8, 33)]:
+        ih, d = helpers.synth_image(w, h, ct, bd, 1 + h, "photo")
+        hdr = helpers.product_image(ih, d).ihdr
+        for pre in (rng.integers(0, 5, h).astype(np.uint8), rng.integers(2, 5, h).astype(np.uint8)):
+            filtered, _, _ = oracle.filter_image(ih, d, oracle.PREDEFINED, 0, pre)
+            assert np.array_equal(ox.unfilter_image(hdr, filtered), d), (ct, bd, w, h)
+        # trailing bytes (less than one scanline): ignored like the reference's iterator
+        extra = np.concatenate([filtered, np.array([3, 1, 2], np.uint8)[:min(3, max(1, d.size // h))]])
+        want = oracle.unfilter_image(ih, extra)
+        assert np.array_equal(ox.unfilter_image(hdr, extra), want), (ct, bd, w, h, "trailing")
+
+
 def test_unfilter_batch_equals_single_images():
     """oxi_unfilter_batch: many streams of one IHDR in one launch (more items than CTA groups) == image by image"""
     import oxipng_b200 as ox
