@@ -82,7 +82,7 @@ if os.environ.get("README"):
     o = oc
     n2 = more[0] if more else None
     lines = ["| What | Result |", "|---|---|",
-             "| Parity | bit-exact vs the CPU oracle through the C ABI (75 GPU tests): 68 reference fixtures × 9 strategies × alpha on/off, ragged / interlaced / sub-byte / 16-bit images, eight whole c5 images (clean, noisy, random), the split-table / wide-table / Entropy+Bigrams kernels, the `optimize_alpha` tier, all reductions host-buffer and resident, the resident `-o2` flow, row-band sharding, 12 threads × mixed geometries. The oracle itself is pinned against PIL/OpenCV decodes of 243 reference fixtures — **not** against the real oxipng (no Rust toolchain here; `tools/ref_dump.rs` closes that gap where cargo exists) |",
+             "| Parity | bit-exact vs the CPU oracle through the C ABI (76 GPU tests): 68 reference fixtures × 9 strategies × alpha on/off, ragged / interlaced / sub-byte / 16-bit images, eight whole c5 images (clean, noisy, random), the split-table / wide-table / Entropy+Bigrams kernels, the `optimize_alpha` tier, all reductions host-buffer and resident, the resident `-o2` flow, row-band sharding, 12 threads × mixed geometries. The oracle itself is pinned against PIL/OpenCV decodes of 243 reference fixtures — **not** against the real oxipng (no Rust toolchain here; `tools/ref_dump.rs` closes that gap where cargo exists) |",
              f"| c5: 1250 × 1024² RGBA8, {{None, Bigrams, BigEnt}} fused, one GPU | **{d['ms_per_step']:.1f} ms = {d['value']:.0f} GB/s raw pixels, {d['images_per_s'] / 1e3:.1f} k images/s** ({pct(d['roofline']['frac'])} of the measured HBM roofline; round 1: {r1['ms_per_step']:.1f} ms, {pct(r1['roofline']['frac'])}); issue / ALU / shared-memory bound, DRAM 10 % |",
              f"| End to end through `oxi_filter_batch` (host buffers) | {e['value']:.1f} GB/s raw pixels with pinned buffers = {100 * cc['e2e_fraction_of_copy_ceiling']:.0f} % of this box's PCIe copy ceiling ({cc['per_rank_GBps']:.0f} GB/s both ways; 95 % on the box of the 2- and 8-GPU records; three filtered streams leave the device per image), {ep['value']:.1f} GB/s with pageable buffers, vs {cpu.get('value', 0):.2f} GB/s for the {cpu.get('cores')}-thread CPU restatement |"]
     if n2:

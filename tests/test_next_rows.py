@@ -82,6 +82,28 @@ def test_unfilter_wide_rows_and_odd_sizes():
         assert np.array_equal(ox.unfilter_image(hdr, extra), want), (ct, bd, w, h, "trailing")
 
 
+def test_unfilter_concurrent_threads():
+    """eight host threads decode different images at once: every call is a cooperative launch on its own stream (PngImage::new
+    runs per file under rayon in the reference's directory mode)"""
+    import concurrent.futures as cf
+    import oxipng_b200 as ox
+    shapes = [(300, 400, 6, 8), (64, 640, 2, 8), (1024, 160, 6, 8), (777, 90, 6, 16), (33, 700, 0, 8), (4000, 60, 2, 8),
+              (128, 1280, 4, 8), (19, 2000, 6, 8)]
+    cases = []
+    for i, (w, h, ct, bd) in enumerate(shapes):
+        ih, d = helpers.synth_image(w, h, ct, bd, 70 + i, "photo")
+        filtered, _, _ = oracle.filter_image(ih, d, oracle.MINSUM if i % 2 else oracle.BASIC, 4)
+        cases.append((helpers.product_image(ih, d).ihdr, filtered, d))
+
+    def work(t):
+        hdr, filtered, d = cases[t % len(cases)]
+        return t, ox.unfilter_image(hdr, filtered)
+
+    with cf.ThreadPoolExecutor(max_workers=8) as ex:
+        for t, got in ex.map(work, range(64)):
+            assert np.array_equal(got, cases[t % len(cases)][2]), t
+
+
 def test_unfilter_batch_equals_single_images():
     """oxi_unfilter_batch: many streams of one IHDR in one launch (more items than CTA groups) == image by image"""
     import oxipng_b200 as ox
