@@ -37,6 +37,9 @@ constexpr int HALF_NT = 256, HALF_OCC = 4;
 constexpr int SC_WIDE = 16;
 __host__ __device__ constexpr int rb_of(int sc) { return (sc & SC_WIDE) ? 6 : 5; } // bits of a range code
 constexpr int HIST_REP = 1;      // copies of each Entropy histogram: one (lanes on the same bin are merged by ATOMS.POPC.INC)
+// an Entropy histogram has 512 counters: counter 256 + d for the signed byte difference d = cur - pred in [-255, 255];
+// the residual value v = d mod 256 is the sum of counters v and v + 256 (entropy_score)
+constexpr uint32_t HIST_BINS = 512, HIST_BYTES = 5 * HIST_BINS * 4;
 constexpr uint32_t PAD = 32;     // zero bytes in front of every staged row (left/upleft of the first pixel)
 constexpr uint32_t SMEM_HDR = 1024;
 constexpr uint32_t SCORE_WORDS = 40;   // s_min/s_ent/s_bgc/s_bge/s_out, 8 words each; three sets rotate row by row
@@ -226,7 +229,7 @@ struct Smem {
     __device__ __forceinline__ uint32_t *s_bge_() const { return sc + 24; } // [5] bigram entropy
     __device__ __forceinline__ uint32_t *s_out_() const { return sc + 32; } // [5] trial flagged: its outliers overflowed the hash table
     uint8_t *rows;     // 3 slots of rb bytes
-    uint32_t *hist;    // [5][HIST_REP][256]
+    uint32_t *hist;    // [5][HIST_BINS]
     uint32_t *table;   // 32768 words = 65536 u16 counters, or (small_tab) the h0_slots-word hash table of whole rows
     uint32_t *small;   // DENSE_WORDS counters of the in-range bigrams of trials 1..4 (layout: dense_off), optional
     uint32_t *ohash;   // [4][HSLOTS] outlier bigrams of trials 1..4: open-addressing tables of (key << 16 | count)
@@ -253,7 +256,7 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot
     s.sc = u; // set 0; sets 1 and 2 follow at SCORE_WORDS strides
     uint8_t *p = base + SMEM_HDR;
     s.hist = reinterpret_cast<uint32_t *>(p); // histograms first: fixed offset, immediates of the atomics
-    if (SC & SC_ENTROPY) p += 5 * HIST_REP * 256 * 4;
+    if (SC & SC_ENTROPY) p += HIST_BYTES;
     s.small = reinterpret_cast<uint32_t *>(p);
     s.ohash = s.small + Dense<rb_of(SC)>::REGION / 4;
     s.table = s.ohash + 4 * HSLOTS;
@@ -270,7 +273,7 @@ __device__ __forceinline__ Smem carve(uint8_t *base, uint32_t rb, uint32_t nslot
 __host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, uint32_t h0_slots, uint32_t nslot = 3, bool split = false) {
     if (split) return SMEM_HDR + SPLIT_BYTES + nslot * rb;
     uint32_t b = SMEM_HDR + nslot * rb;
-    if (sc & SC_ENTROPY) b += 5 * HIST_REP * 256 * 4;
+    if (sc & SC_ENTROPY) b += HIST_BYTES;
     if (sc & SC_BIGRAM)
         b += h0_slots ? ((sc & SC_HALF) ? 0u : h0_slots * 4) + ((sc & SC_WIDE) ? Dense<6>::SMALL : Dense<5>::SMALL) : 65536 * 2;
     return b;
@@ -350,50 +353,49 @@ __device__ __forceinline__ uint32_t scale4(uint32_t v, uint32_t four) {
     asm("mul.lo.u32 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(four));
     return d;
 }
-template <uint32_t HB>
-__device__ __forceinline__ void hist_word(uint32_t r, uint32_t four) {
-#ifdef OXI_HIST_OLD
-    const uint32_t lo = (r * 4u) & 0xFCFCFCFCu, hi = (r >> 6) & 0x03030303u;
-    smem_inc_at<HB>(prmt(lo, hi, 0xCC40u));
-    smem_inc_at<HB>(prmt(lo, hi, 0xDD51u));
-    smem_inc_at<HB>(prmt(lo, hi, 0xEE62u));
-    smem_inc_at<HB>(prmt(lo, hi, 0xFF73u));
-#else
-    // one PRMT per byte (zero-extended value) on the ALU pipe, the "times four" as IMAD.SHL on the otherwise idle FMA
-    // pipe: the scorer is bound by the ALU pipe (82 % in round 2's capture), and the pre-scaled lo / hi words of the
-    // earlier form cost three more ALU operations per word
-    smem_inc_at<HB>(scale4(prmt(r, 0u, 0x4440u), four));
-    smem_inc_at<HB>(scale4(prmt(r, 0u, 0x4441u), four));
-    smem_inc_at<HB>(scale4(prmt(r, 0u, 0x4442u), four));
-    smem_inc_at<HB>(scale4(prmt(r, 0u, 0x4443u), four));
-#endif
+// The counters of one row word for all five filters.  Per byte: the value x is extracted once (PRMT) and scaled
+// (IMAD: x*4), per filter the predictor byte p is extracted (PRMT) and the counter address formed by one multiply-add
+// ((256 + x)*4 - p*4) on the FMA pipe; the histogram base is the atomic's immediate.  No bytewise
+// subtraction: `__vsub4` costs three ALU operations per word and filter on the pipe that bounds this scorer (82 %).
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) { // a * b + c, b opaque: stays an IMAD
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
-template <uint32_t HB>
-__device__ __forceinline__ void hist_word_tail(uint32_t r, int nvalid) {
-    for (int j = 0; j < nvalid; j++) smem_inc(HB + (((r >> (8 * j)) & 255u) << 2));
+template <int K>
+__device__ __forceinline__ void hist_byte(uint32_t x, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4, uint32_t four, uint32_t neg4) {
+    const uint32_t xq = mad_lo(prmt(x, 0u, 0x4440u + K), four, 1024u); // (256 + x) * 4: the register part stays positive
+    smem_inc_at<HIST_ADDR + 0 * 2048u>(xq);
+    smem_inc_at<HIST_ADDR + 1 * 2048u>(mad_lo(prmt(p1, 0u, 0x4440u + K), neg4, xq));
+    smem_inc_at<HIST_ADDR + 2 * 2048u>(mad_lo(prmt(p2, 0u, 0x4440u + K), neg4, xq));
+    smem_inc_at<HIST_ADDR + 3 * 2048u>(mad_lo(prmt(p3, 0u, 0x4440u + K), neg4, xq));
+    smem_inc_at<HIST_ADDR + 4 * 2048u>(mad_lo(prmt(p4, 0u, 0x4440u + K), neg4, xq));
 }
 template <int D, bool TAIL>
 __device__ __forceinline__ void entropy_chunk(const uint8_t *cur, const uint8_t *up, uint32_t c, int valid, uint32_t shift,
                                               uint32_t four) {
     const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
+    const uint32_t neg4 = 0u - four;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t x = cw.w[k + 2], u = uw.w[k + 2], l = left_word<D>(cw, k, shift), ul = left_word<D>(uw, k, shift);
-        const uint32_t r1 = __vsub4(x, l), r2 = __vsub4(x, u), r3 = __vsub4(x, __vhaddu4(l, u)), r4 = __vsub4(x, paeth4(l, u, ul));
+        const uint32_t pa = __vhaddu4(l, u), pp = paeth4(l, u, ul);
         if (!TAIL) {
-            hist_word<HIST_ADDR + 0 * 1024u>(x, four);
-            hist_word<HIST_ADDR + 1 * 1024u>(r1, four);
-            hist_word<HIST_ADDR + 2 * 1024u>(r2, four);
-            hist_word<HIST_ADDR + 3 * 1024u>(r3, four);
-            hist_word<HIST_ADDR + 4 * 1024u>(r4, four);
+            hist_byte<0>(x, l, u, pa, pp, four, neg4);
+            hist_byte<1>(x, l, u, pa, pp, four, neg4);
+            hist_byte<2>(x, l, u, pa, pp, four, neg4);
+            hist_byte<3>(x, l, u, pa, pp, four, neg4);
         } else {
             const int nv = min(valid - 4 * k, 4);
             if (nv <= 0) break;
-            hist_word_tail<HIST_ADDR + 0 * 1024u>(x, nv);
-            hist_word_tail<HIST_ADDR + 1 * 1024u>(r1, nv);
-            hist_word_tail<HIST_ADDR + 2 * 1024u>(r2, nv);
-            hist_word_tail<HIST_ADDR + 3 * 1024u>(r3, nv);
-            hist_word_tail<HIST_ADDR + 4 * 1024u>(r4, nv);
+            for (int j = 0; j < nv; j++) {
+                const uint32_t xb = (x >> (8 * j)) & 255u;
+                smem_inc(HIST_ADDR + 0 * 2048u + 1024u + (xb << 2));
+                smem_inc(HIST_ADDR + 1 * 2048u + 1024u + ((xb - ((l >> (8 * j)) & 255u)) << 2));
+                smem_inc(HIST_ADDR + 2 * 2048u + 1024u + ((xb - ((u >> (8 * j)) & 255u)) << 2));
+                smem_inc(HIST_ADDR + 3 * 2048u + 1024u + ((xb - ((pa >> (8 * j)) & 255u)) << 2));
+                smem_inc(HIST_ADDR + 4 * 2048u + 1024u + ((xb - ((pp >> (8 * j)) & 255u)) << 2));
+            }
         }
     }
 }
@@ -410,8 +412,10 @@ template <int NT>
 __device__ __forceinline__ void entropy_score(uint32_t *hist, uint32_t *s_ent) {
     for (uint32_t idx = threadIdx.x; idx < 5 * 256; idx += NT) {
         const uint32_t f = idx >> 8, v = idx & 255u;
-        const uint32_t cnt = hist[idx] + ((v == f) ? 1u : 0u); // + the filter-type byte that leads the filtered line
-        hist[idx] = 0;
+        uint32_t *h = hist + f * HIST_BINS + v; // residual v: differences v - 256 (counter v) and v (counter 256 + v)
+        const uint32_t cnt = h[0] + h[256] + ((v == f) ? 1u : 0u); // + the filter-type byte that leads the filtered line
+        h[0] = 0;
+        h[256] = 0;
         uint32_t s = warp_sum(ilog2i(cnt | (cnt == 0)) * (cnt != 0));
         if ((threadIdx.x & 31) == 0) atomicAdd(&s_ent[f], s);
     }
@@ -1268,7 +1272,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_WIDE) ? 2 : (SC & SC
     for (uint32_t i = tid; i < NS * PAD / 4; i += NT) // zero the left pad of each slot (never written again)
         reinterpret_cast<uint32_t *>(sm.rows + (i / (PAD / 4)) * (size_t)P.rb)[i % (PAD / 4)] = 0;
     if (SC & SC_ENTROPY)
-        for (uint32_t i = tid; i < 5 * HIST_REP * 256; i += NT) sm.hist[i] = 0;
+        for (uint32_t i = tid; i < 5 * HIST_BINS; i += NT) sm.hist[i] = 0;
     if (SC & SC_BIGRAM) {
         for (uint32_t i = tid; i < (P.small_tab == 1u ? P.h0_slots : split ? SPLIT_BYTES / 4 : 32768u); i += NT) sm.table[i] = 0;
         if (P.small_tab == 1u)
@@ -1384,7 +1388,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_WIDE) ? 2 : (SC & SC
                         split_done = true;
                     }
                     else if ((SC & SC_HALF) || P.small_tab == 1u) {
-                        nz |= bigram_row_small<D, NT, SMEM_WIN + SMEM_HDR + ((SC & SC_ENTROPY) ? 5u * HIST_REP * 256u * 4u : 0u), rb_of(SC)>(cur, up, len, shift, bpp, sr, P.h0_slots, pf);
+                        nz |= bigram_row_small<D, NT, SMEM_WIN + SMEM_HDR + ((SC & SC_ENTROPY) ? HIST_BYTES : 0u), rb_of(SC)>(cur, up, len, shift, bpp, sr, P.h0_slots, pf);
                         small_flow = true;
                     }
                     else if (wpt <= 1) bigram_row<D, NT, 1>(cur, up, len, shift, bpp, sm.table, sr.s_bgc_(), sr.s_bge_());
