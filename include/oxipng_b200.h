@@ -177,7 +177,9 @@ int oxi_unfilter_image(const oxi_ihdr *, const uint8_t *filtered, size_t len, ui
  * walk the images, so the device is filled even though one image's rows form a dependency chain. */
 int oxi_unfilter_batch(const oxi_ihdr *, const uint8_t *filtered, size_t len, size_t n_images, uint8_t *out, size_t *out_len);
 /* the same with the inflated stream already in HBM: d_filtered (len bytes) and d_out are device pointers on `device`,
- * the work is enqueued on `stream`; only the few-byte "invalid filter type" flag is read back (synchronises) */
+ * the work is enqueued on `stream`; only the few-byte "invalid filter type" flag is read back (synchronises).
+ * Both pointers must be 16-byte aligned (OXI_E_ARG otherwise); the stream is read in aligned 4-byte words, i.e. up to
+ * 3 bytes past `len` inside the word that holds the last byte.  Scanlines of 16 MB and more: OXI_E_UNSUPPORTED. */
 int oxi_unfilter_image_device(int device, void *stream, const oxi_ihdr *, const uint8_t *d_filtered, size_t len,
                               uint8_t *d_out, size_t *out_len);
 int oxi_unfilter_batch_device(int device, void *stream, const oxi_ihdr *, const uint8_t *d_filtered, size_t len, size_t n_images,
