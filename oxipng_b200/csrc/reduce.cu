@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(RT) k_deinterlace(const uint8_t *__restrict__ 
 // c+1 and stores row j of chunk c-1 (double-buffered windows and result arrays, branch-free: rows and pixels that do
 // not exist are clipped by one unsigned compare on tile-relative 32-bit offsets), so a lone warp per scheduler has
 // independent work to issue while the dependency chain of the step waits.
-constexpr int UF_WARPS = 4, UF_RAW = 33, UF_SUB = 8, UF_RING = 64;
+constexpr int UF_WARPS = 4, UF_RAW = 33, UF_RING = 64;
 // per-warp shared memory, in words: two windows x 32 rows, two result buffers of one or two [32][CH+1] arrays
 constexpr int uf_warp_words(int bpp) { return 2 * 32 * UF_RAW + 2 * (bpp > 4 ? 2 * 32 * 17 : 32 * 33); }
 constexpr uint32_t UF_MAX_ROW = 1u << 24; // tile-relative offsets are 32-bit: rows of 16 MB and more are refused
@@ -683,8 +683,10 @@ struct UfTile {
     uint32_t gen;  // request number of this tile (dep tiles)
 };
 
-// MODE 0: None/Sub/Up rows only; 1: + Average; 2: + Paeth
-template <int BPP, int MODE>
+// MODE 0: None/Sub/Up rows only; 1: + Average; 2: + Paeth.  SUB: steps per sub-chunk (8 or 16) = the unrolled body and the
+// granularity of the boundary hand-over: 16 gives a lone warp more independent work per basic block (one image: -8..12 %),
+// 8 keeps the body small when three CTAs share an SM's instruction cache (batches) and the registers of 6/8-byte pixels
+template <int BPP, int MODE, int SUB>
 __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t lane) {
     constexpr int N1 = BPP > 4 ? BPP - 4 : 0;
     constexpr int CH = BPP > 4 ? 16 : 32;          // pixels (= steps) per chunk
@@ -723,7 +725,7 @@ __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t
     const int st_row = CH == 16 ? (int)(lane & 16u) : 0, st_px = CH == 16 ? (int)(lane & 15u) : (int)lane;
 
     uint32_t l0 = 0, l1 = 0, ul0 = 0, ul1 = 0; // rebuilt left pixel, upleft pixel
-    // boundary pixels of the current sub-chunk (lanes 0..UF_SUB-1), taken from the mailbox ring
+    // boundary pixels of the current sub-chunk (lanes 0..SUB-1), taken from the mailbox ring
     uint32_t c0 = 0, c1 = 0;
     volatile UfSlot *slot = T.slot;
     if (T.dep) { // post the request; the poller starts on it when it sees the new request number
@@ -754,15 +756,15 @@ __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t
         const int st_add = ((int)(c * CH) - CH + st_px) * BPP; // chunk c-1 ("-1": nothing passes the range check)
         const int x0 = (int)(c * CH) - (int)T.delta; // this lane's pixel at the chunk's first step
 #pragma unroll 1
-        for (int q = 0; q < CH / UF_SUB; q++) {
+        for (int q = 0; q < CH / SUB; q++) {
             if (T.dep) {
-                const uint32_t xb = c * CH + q * UF_SUB; // lane 0's row is at delta 0: step == pixel
+                const uint32_t xb = c * CH + q * SUB; // lane 0's row is at delta 0: step == pixel
                 if (xb < T.npix) {
-                    const uint32_t need = min(xb + UF_SUB, T.npix);
+                    const uint32_t need = min(xb + SUB, T.npix);
                     while (slot->avail < need) {}
                     // (no fence: the ring words were written before `avail` by the same warp, and a warp's volatile
                     // shared-memory accesses are performed in program order)
-                    if (lane < UF_SUB) {
+                    if (lane < SUB) {
                         c0 = slot->ring0[(xb + lane) & (UF_RING - 1)];
                         if (N1) c1 = slot->ring1[(xb + lane) & (UF_RING - 1)];
                     }
@@ -773,10 +775,10 @@ __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t
             // every shared-memory read of the sub-chunk up front (ptxas keeps LDS behind an earlier LDGSTS, so a load
             // inside the steps would sit right in front of its use): the filtered pixels of the sub-chunk and the result
             // words this lane stores for chunk c-1
-            uint32_t d0[UF_SUB], d1[UF_SUB], s0[UF_SUB], s1[UF_SUB];
+            uint32_t d0[SUB], d1[SUB], s0[SUB], s1[SUB];
 #pragma unroll
-            for (int jj = 0; jj < UF_SUB; jj++) {
-                const int j = q * UF_SUB + jj;
+            for (int jj = 0; jj < SUB; jj++) {
+                const int j = q * SUB + jj;
                 const uint32_t o = mis + j * BPP; // bytes [o, o + BPP) of the window
                 const uint32_t *wp = lb + (o >> 2);
                 const uint32_t w0 = wp[0], w1 = wp[1];
@@ -786,8 +788,8 @@ __device__ __noinline__ void uf_run(const UfTile T, uint32_t *sm, const uint32_t
                 s1[jj] = N1 ? sb[j * OS + 32 * OS] : 0u;
             }
 #pragma unroll
-            for (int jj = 0; jj < UF_SUB; jj++) {
-                const int j = q * UF_SUB + jj;
+            for (int jj = 0; jj < SUB; jj++) {
+                const int j = q * SUB + jj;
                 // pixel above: lane l-1's result of the previous step; lane 0: the boundary word
                 uint32_t a0 = __shfl_up_sync(0xffffffffu, l0, 1);
                 uint32_t a1 = N1 ? __shfl_up_sync(0xffffffffu, l1, 1) : 0u;
@@ -882,7 +884,7 @@ __device__ __noinline__ void uf_poller(volatile UfCtl *ctl, const uint64_t ent_w
     }
 }
 
-template <int BPP>
+template <int BPP, int SUB>
 __global__ void __launch_bounds__((UF_WARPS + 1) * 32) k_unfilter(Geom g, const uint8_t *__restrict__ in, uint8_t *out,
                                                             uint64_t n_images, uint64_t in_stride, ScanState *st,
                                                             unsigned long long *ent, UfPlan plan) {
@@ -945,9 +947,9 @@ __global__ void __launch_bounds__((UF_WARPS + 1) * 32) k_unfilter(Geom g, const 
 #ifdef UF_TRACE
         unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
 #endif
-        if (any_paeth) uf_run<BPP, 2>(T, sm, lane);
-        else if (any_avg) uf_run<BPP, 1>(T, sm, lane);
-        else uf_run<BPP, 0>(T, sm, lane);
+        if (any_paeth) uf_run<BPP, 2, SUB>(T, sm, lane);
+        else if (any_avg) uf_run<BPP, 1, SUB>(T, sm, lane);
+        else uf_run<BPP, 0, SUB>(T, sm, lane);
 #ifdef UF_TRACE
         unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (lane == 0 && t < 128) { st->hist[t] = t0; st->hist[128 + t] = t1; }
@@ -1571,13 +1573,14 @@ static int unfilter_streams(const oxi_ihdr *h, const uint8_t *filtered, size_t l
     if (cudaMemsetAsync(ent, 0, ent_bytes, call.stream) != cudaSuccess) return fail(OXI_E_CUDA, "memset(boundary words)");
     {
         const void *fn = nullptr;
+        const bool wide_body = n_images == 1; // one image: a lone warp per scheduler (see uf_run, SUB)
         switch (g.bpp) {
-        case 1: fn = (const void *)k_unfilter<1>; break;
-        case 2: fn = (const void *)k_unfilter<2>; break;
-        case 3: fn = (const void *)k_unfilter<3>; break;
-        case 4: fn = (const void *)k_unfilter<4>; break;
-        case 6: fn = (const void *)k_unfilter<6>; break;
-        case 8: fn = (const void *)k_unfilter<8>; break;
+        case 1: fn = wide_body ? (const void *)k_unfilter<1, 16> : (const void *)k_unfilter<1, 8>; break;
+        case 2: fn = wide_body ? (const void *)k_unfilter<2, 16> : (const void *)k_unfilter<2, 8>; break;
+        case 3: fn = wide_body ? (const void *)k_unfilter<3, 16> : (const void *)k_unfilter<3, 8>; break;
+        case 4: fn = wide_body ? (const void *)k_unfilter<4, 16> : (const void *)k_unfilter<4, 8>; break;
+        case 6: fn = (const void *)k_unfilter<6, 8>; break;
+        case 8: fn = (const void *)k_unfilter<8, 8>; break;
         default: return fail(OXI_E_ARG, "unsupported filter bpp");
         }
         // always the same value for a given instantiation: concurrent callers cannot shrink each other's limit
