@@ -81,5 +81,9 @@ cudaError_t slot_begin(Slot *s, cudaStream_t st);
 // give the slot back while work using its buffers is still queued on `st` (device-resident calls)
 void release_slot_async(DeviceCtx *c, Slot *s, cudaStream_t st);
 cudaError_t grow(uint8_t **p, size_t *cap, size_t need);
+// ordinary (pageable) caller memory is staged through the slot's pinned buffers by several copy threads (capi.cu)
+bool is_pageable(const void *p);
+void par_memcpy(uint8_t *dst, const uint8_t *src, size_t n);
+cudaError_t grow_pinned(uint8_t **p, size_t *cap, size_t need);
 
 } // namespace oxi
