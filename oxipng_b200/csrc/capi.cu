@@ -289,7 +289,21 @@ void par_memcpy(uint8_t *dst, const uint8_t *src, size_t n) {
     }
     pool.cv.notify_all();
     memcpy(dst, src, per <= n ? per : n);
-    while (left.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+    // wait for the other pieces, helping with whatever is still queued (also keeps a forked child, which inherits the
+    // pool object but not its threads, from waiting forever)
+    while (left.load(std::memory_order_acquire) != 0) {
+        CopyPool::Job j{nullptr, nullptr, 0, nullptr};
+        {
+            std::lock_guard<std::mutex> lk(pool.mu);
+            if (!pool.q.empty()) { j = pool.q.front(); pool.q.pop_front(); }
+        }
+        if (j.left) {
+            memcpy(j.dst, j.src, j.n);
+            j.left->fetch_sub(1, std::memory_order_release);
+        } else {
+            std::this_thread::yield();
+        }
+    }
 }
 cudaError_t grow_pinned(uint8_t **p, size_t *cap, size_t need) {
     if (need <= *cap) return cudaSuccess;
