@@ -61,6 +61,7 @@ struct FastParams {
     const uint8_t *img_class; // optional per-image class written by k_spread_probe (0: residuals within +-16, 1: wider)
     uint32_t want_class;      // the class this launch takes
     uint32_t four;      // the constant 4, opaque to the compiler (scale4)
+    uint32_t two31;     // the constant 2^31, opaque to the compiler (havg4)
     uint32_t small_tab; // bigram scorer: 1 = the dense-table layout (rows <= 16384 bytes), 2 = the split-table layout (<= 32768)
 };
 
@@ -285,6 +286,16 @@ __host__ inline uint32_t smem_bytes_for(int sc, uint32_t rb, uint32_t h0_slots, 
 // it into the reference's score 128*bytes - S_f + f (the filter-type byte f counts |f| = f, png/mod.rs:409-414).
 // S_0 also answers the all-zero-row test: ||x| - 128| is 128 only for x = 0, so S_0 = 128 * bytes iff the row is zero.
 // S0: bpp = 4 (the funnel shift that forms "left" is by zero bits: a plain register pick).
+// floor((a + b) / 2) per byte = (a & b) + (((a ^ b) & 0xFE..) >> 1); the shift as a multiply-high by 2^31 -- handed in as a
+// kernel parameter so that it stays an IMAD.HI on the FMA pipe -- and the mask folded into the XOR's LOP3: two ALU
+// operations instead of the four of __vhaddu4 on the pipe that bounds the MinSum and Entropy scorers
+__device__ __forceinline__ uint32_t havg4(uint32_t a, uint32_t b, uint32_t two31) {
+#ifdef OXI_HAVG_OLD
+    return __vhaddu4(a, b);
+#else
+    return (a & b) + __umulhi((a ^ b) & 0xFEFEFEFEu, two31);
+#endif
+}
 __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t acc) { // acc + sum_i |a_i - b_i| (bytes)
     uint32_t d;
     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
@@ -292,7 +303,7 @@ __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t ac
 }
 template <int D, bool TAIL, bool S0>
 __device__ __forceinline__ void minsum_chunk(const uint8_t *cur, const uint8_t *up, uint32_t c, int valid, uint32_t shift,
-                                             uint32_t (&a)[5]) {
+                                             uint32_t (&a)[5], uint32_t two31) {
     const Chunk cw = load_chunk(cur, c), uw = load_chunk(up, c);
     const uint32_t H = 0x80808080u;
 #pragma unroll
@@ -316,22 +327,22 @@ __device__ __forceinline__ void minsum_chunk(const uint8_t *cur, const uint8_t *
         a[0] = sad4_acc(x, H, a[0]);
         a[1] = sad4_acc(__vabsdiffu4(x, l), H, a[1]);
         a[2] = sad4_acc(__vabsdiffu4(x, u), H, a[2]);
-        a[3] = sad4_acc(__vabsdiffu4(x, __vhaddu4(l, u)), H, a[3]);
+        a[3] = sad4_acc(__vabsdiffu4(x, havg4(l, u, two31)), H, a[3]);
         a[4] = sad4_acc(__vabsdiffu4(x, paeth4(l, u, ul)), H, a[4]);
 #endif
     }
 }
 template <int D, int NT>
 __device__ __forceinline__ void minsum_pass(const uint8_t *cur, const uint8_t *up, uint32_t len, uint32_t shift,
-                                            uint32_t *s_min) {
+                                            uint32_t *s_min, uint32_t two31) {
     const uint32_t nfull = len >> 4; // complete 16-byte chunks: no masking in the main loop
     uint32_t a[5] = {0, 0, 0, 0, 0};
     if (D == 1 && shift == 0) {
-        for (uint32_t c = threadIdx.x; c < nfull; c += NT) minsum_chunk<D, false, true>(cur, up, c, 16, shift, a);
+        for (uint32_t c = threadIdx.x; c < nfull; c += NT) minsum_chunk<D, false, true>(cur, up, c, 16, shift, a, two31);
     } else {
-        for (uint32_t c = threadIdx.x; c < nfull; c += NT) minsum_chunk<D, false, false>(cur, up, c, 16, shift, a);
+        for (uint32_t c = threadIdx.x; c < nfull; c += NT) minsum_chunk<D, false, false>(cur, up, c, 16, shift, a, two31);
     }
-    if ((len & 15u) && threadIdx.x == (nfull % NT)) minsum_chunk<D, true, false>(cur, up, nfull, (int)(len & 15u), shift, a);
+    if ((len & 15u) && threadIdx.x == (nfull % NT)) minsum_chunk<D, true, false>(cur, up, nfull, (int)(len & 15u), shift, a, two31);
     a[0] = warp_sum(a[0]); a[1] = warp_sum(a[1]); a[2] = warp_sum(a[2]); a[3] = warp_sum(a[3]); a[4] = warp_sum(a[4]);
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&s_min[0], a[0]); atomicAdd(&s_min[1], a[1]); atomicAdd(&s_min[2], a[2]);
@@ -379,7 +390,7 @@ __device__ __forceinline__ void entropy_chunk(const uint8_t *cur, const uint8_t 
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t x = cw.w[k + 2], u = uw.w[k + 2], l = left_word<D>(cw, k, shift), ul = left_word<D>(uw, k, shift);
-        const uint32_t pa = __vhaddu4(l, u), pp = paeth4(l, u, ul);
+        const uint32_t pa = havg4(l, u, neg4 << 29), pp = paeth4(l, u, ul); // (-4) << 29 = 2^31, opaque like `four`
         if (!TAIL) {
             hist_byte<0>(x, l, u, pa, pp, four, neg4);
             hist_byte<1>(x, l, u, pa, pp, four, neg4);
@@ -1375,7 +1386,7 @@ __global__ void __launch_bounds__(threads_for(SC), (SC & SC_WIDE) ? 2 : (SC & SC
                 if (tid < (int)SCORE_WORDS) sm.sc[set_next * SCORE_WORDS + tid] = 0;
                 uint32_t nz = 0;
                 bool small_flow = false, split_done = false;
-                if (SC & SC_MINSUM) minsum_pass<D, NT>(cur, up, len, shift, sr.s_min_());
+                if (SC & SC_MINSUM) minsum_pass<D, NT>(cur, up, len, shift, sr.s_min_(), P.two31);
                 if (SC & SC_ENTROPY) {
                     entropy_pass<D, NT>(cur, up, len, shift, sm.hist, P.four);
                     __syncthreads();
@@ -2033,6 +2044,7 @@ static cudaError_t launch_fast_variant(const LaunchCtx &ctx, const Geom &g, cons
     P.rb = slot_bytes(g);
     P.shift = 8 * (g.bpp % 4);
     P.four = 4;
+    P.two31 = 0x80000000u;
     P.small_tab = split ? 2 : small_tab ? 1 : 0;
     P.h0_slots = small_tab ? h0 : 0;
     P.img_class = img_class;
